@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py -- flux cell-updates/s of the fused per-cell flux chain (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4|C2|C3|C5] [--impl reference]
+
+A "step" is one coupling step (early + normal phase fused: fc_step_all) over the synthetic exchange grid.
+Default workload C4 = BASELINE.json configs[3], the configuration the metric's roofline target is quoted on:
+10^7 cells per grid (t,u,v), CCLM formula set, all fluxes fused, monthly evaporation bias, area-weighted
+diagnostics; for N>1 the grid is sharded into contiguous ranges (strong scaling: the 10^7 cells are fixed) and
+the diagnostics are reduced with NCCL.  One JSON line on stdout (rank 0).
+
+`value`  : device-resident throughput, CUDA events on the launching stream, max over ranks.
+`e2e`    : same metric through the C ABI with HOST (pinned) arrays: H2D + kernel + D2H inside the timed region.
+`roofline`: fused kernel only (event pairs around every launch inside the timed region) vs measured HBM peak.
+`cpu_baseline` / --impl reference: the CPU oracle arranged like the reference (one pass per quantity, one
+scalar call per cell), P independent ranks = all host threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (formula_set, cells per grid, S, bias, averaging, diagnostics, description)
+    "C2": ("MOM5", 20_000, 1, True, False, False, "Baltic stand-in 20k cells/grid, MOM5 coefficients + monthly evaporation bias"),
+    "C3": ("RCO", 1_000_000, 1, False, False, False, "RCO (Meier 1999) formula set, 1e6 cells/grid"),
+    "C4": ("CCLM", 10_000_000, 1, True, False, True, "1e7 cells/grid, CCLM set, all fluxes fused + bias + diagnostics (NCCL all-reduce for N>1)"),
+    "C5": ("CCLM", 10_000_000, 2, True, True, False, "1e7 cells/grid, CCLM set, open water + ice (S=2) with area-fraction averaging, device resident"),
+}
+METRIC = "flux cell-updates/s per coupling step; achieved HBM GB/s vs B200 peak"
+UNIT = "cell-updates/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        self.thr = threading.Thread(target=pump, daemon=True)
+        self.thr.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_scenario(workload, offset_size=None, cells=None):
+    from components.flux_calculator_b200.synthetic import Scenario
+    fset, n, S, bias, avg, diag, _ = WORKLOADS[workload]
+    if cells is not None:
+        n = cells
+    off, size = offset_size if offset_size else (0, n)
+    return Scenario(fset, n=(size, size, size), S=S, bias=bias, averaging=avg, offset=(off, off, off))
+
+
+def native_oracle():
+    """rebuild the release-like oracle with -march=native for THIS host (falls back to the shipped x86-64-v3 build)"""
+    import ctypes as C
+    from oracle_py import ORACLE_DIR
+    out = os.path.join(ORACLE_DIR, "_native")
+    try:
+        os.makedirs(out, exist_ok=True)
+        so = os.path.join(out, "liboracle_fast.so")
+        subprocess.check_call(["gcc", "-std=c11", "-O3", "-march=native", "-ffast-math", "-fPIC", "-shared", "-o", so,
+                               os.path.join(ORACLE_DIR, "flux_oracle.c"), os.path.join(ORACLE_DIR, "cpu_baseline.c"),
+                               "-lm", "-lpthread"], stderr=subprocess.DEVNULL)
+        C.CDLL(so)
+        return so, "-O3 -march=native -ffast-math"
+    except Exception:
+        return os.path.join(ORACLE_DIR, "liboracle_fast.so"), "-O3 -march=x86-64-v3 -ffast-math"
+
+
+def cpu_arm(workload, steps, warmup, sample_cells, threads=None):
+    """the reference's CPU path (oracle port in the reference's loop structure) on all host threads"""
+    import oracle_py
+    so, flags = native_oracle()
+    ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    P = threads or ncores
+    fset, n, S, bias, avg, diag, _ = WORKLOADS[workload]
+    cells = min(n, sample_cells)
+    sc = build_scenario(workload, cells=cells)
+    ins, outs = sc.clone()
+    orc = oracle_py.Oracle(sc.n, sc.S, fast=True, lib_path=so)
+    sc.apply(orc, ins, outs)
+    for _ in range(max(1, min(warmup, 2))):
+        orc.run_ranks(P, 1, 600, 0)
+    times = []
+    for k in range(steps):
+        t0 = time.perf_counter()
+        orc.run_ranks(P, 1, 600, 600 * k)
+        times.append(time.perf_counter() - t0)
+    t = float(np.mean(times))
+    return {"value": cells / t, "unit": UNIT, "cores": P, "kind": "port",
+            "sample": "%d cells/grid x %d steps of workload %s, %d ranks (threads) each owning a contiguous range, gcc %s"
+                      % (cells, steps, workload, P, flags),
+            "ms_per_step": t * 1e3}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return 0
+    wl = args.workload
+    sample = args.cpu_sample_cells or 4_000_000
+    res = cpu_arm(wl, args.steps, args.warmup, sample)
+    fset, n, S, bias, avg, diag, desc = WORKLOADS[wl]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %s" % (wl, desc), "cells_per_grid": n, "formula_set": fset, "surface_types": S,
+                   "note": "reference cannot be compiled here (Fortran+MPI+netCDF+OASIS, no Fortran compiler): CPU arm is the oracle port in the reference's loop structure"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--cells", type=int, default=None, help="override cells per grid (debug)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-sample-cells", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist   # control plane only (barrier, max over ranks, unique-id broadcast)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend="gloo", rank=rank, world_size=world)
+
+    import components.flux_calculator_b200 as m
+    from components.flux_calculator_b200 import DeviceArray, pinned_empty
+
+    if m.lib.fc_device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 device visible; the flux calculator has no CPU fallback")
+    device = local_rank
+    fset, n_total, S, bias, avg, diag, desc = WORKLOADS[args.workload]
+    if args.cells:
+        n_total = args.cells
+    off, size = m.shard_range(n_total, rank, world, 512)
+    sc = build_scenario(args.workload, (off, size), cells=n_total)
+
+    # ---------------- device-resident context (value, roofline) ----------------
+    g_in, g_out = sc.clone()
+    fc = m.FluxCalculator(sc.n, sc.S, device=device)
+    wrapped = sc.apply(fc, g_in, g_out, wrap=lambda a: DeviceArray.from_numpy(a, device))
+    if diag:
+        for g in (1, 2, 3):
+            fc.set_area(g, sc.area[g])
+        fc.set_option("diagnostics", 1)
+    fc.prepare()
+    assert fc.info("fused") == 1, "bench workload must run on the fused kernel"
+    if world > 1 and diag:
+        import torch
+        uid = [m.comm_get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        fc.comm_init(uid[0], rank, world)
+
+    def one_step(k):
+        fc.step_all(600 * k)
+        if diag and world > 1:
+            fc.allreduce_diagnostics()
+
+    def barrier():
+        fc.synchronize()
+        if dist:
+            dist.barrier()
+
+    for k in range(args.warmup):
+        one_step(k)
+    barrier()
+    launches0 = fc.info("launches")
+    fc.set_option("profile_kernel", 1)
+    sampler = ClockSampler(device)
+    sampler.start()
+    barrier()
+    fc.event_record(0)
+    for k in range(args.steps):
+        one_step(args.warmup + k)
+    fc.event_record(1)
+    ms_total = fc.event_elapsed_ms()
+    barrier()
+    clocks = sampler.stop()
+    kern_ms, kern_cnt = fc.kernel_time_ms()
+    fc.set_option("profile_kernel", 0)
+    launches = fc.info("launches") - launches0
+    if dist:
+        import torch
+        t = torch.tensor([ms_total, kern_ms / max(kern_cnt, 1)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, kern_avg_ms = float(t[0]), float(t[1])
+        lt = torch.tensor([launches], dtype=torch.int64)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+        launches = int(lt[0])
+    else:
+        kern_avg_ms = kern_ms / max(kern_cnt, 1)
+    ms_per_step = ms_total / args.steps
+    value = n_total / (ms_per_step * 1e-3)
+
+    bytes_per_cell = fc.info("bytes_per_cell")
+    peak, peak_src = measured_peaks()
+    # the slowest rank's kernel processes `size` cells of each grid per launch
+    max_size = max(m.shard_range(n_total, r, world, 512)[1] for r in range(world))
+    achieved = bytes_per_cell * max_size / (kern_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fused_step_kernel", "kernel_ms": kern_avg_ms,
+                "algorithmic_bytes_per_cell": bytes_per_cell, "cells_per_launch": max_size, "peak_source": peak_src}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("workload") == args.workload and tr.get("cells_per_launch") == max_size:
+            roofline["traffic"] = tr["dram_bytes_per_launch"]
+            roofline["traffic_source"] = tr.get("source")
+    except Exception:
+        pass
+
+    # parity spot check of what was just timed (first 4096 cells of every output vs the oracle)
+    parity = None
+    if rank == 0:
+        from oracle_py import Oracle
+        from tolerances import check_field
+        ns = min(4096, size)
+        small = build_scenario(args.workload, (off, ns), cells=n_total)
+        o_in, o_out = small.clone()
+        orc = Oracle(small.n, small.S)
+        small.apply(orc, o_in, o_out)
+        orc.step_all(600 * (args.warmup + args.steps - 1))
+        worst = 0.0
+        for k in sorted(o_out):
+            got = wrapped[id(g_out[k])].download()[:ns]
+            worst = max(worst, check_field(k[2], got, o_out[k], fset))
+        parity = {"checked_fields": len(o_out), "cells": ns, "max_rel_err": worst, "tolerance": "1e-12 rel + 1e-12*scale"}
+
+    diag_sample = None
+    if diag:
+        s_, mn_, mx_ = fc.diagnostics(1, 1, "HSEN")
+        diag_sample = {"HSEN_type1": {"sum_area_x": s_, "min": mn_, "max": mx_}}
+
+    # ---------------- end-to-end through the C ABI with host arrays ----------------
+    e2e = None
+    if not args.no_e2e:
+        for w in wrapped.values():
+            w.free()
+        fc.close()
+        h_in, h_out = {}, {}
+        memo = {}
+        def pin(a):
+            if id(a) not in memo:
+                p = pinned_empty(a.size)
+                p[:] = a
+                memo[id(a)] = p
+            return memo[id(a)]
+        for k, a in g_in.items():
+            h_in[k] = pin(a)
+        for k, a in g_out.items():
+            h_out[k] = pin(a)
+        fh = m.FluxCalculator(sc.n, sc.S, device=device)
+        sc.apply(fh, h_in, h_out)
+        if diag:
+            for g in (1, 2, 3):
+                fh.set_area(g, sc.area[g])
+            fh.set_option("diagnostics", 1)
+        fh.prepare()
+        fh.step_all(0)
+        fh.synchronize()
+        if dist:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            fh.step_all(600 * (k + 1))
+            chk = float(h_out[(1, 1, "HSEN")][0])     # the host reads a result of every step
+        fh.synchronize()
+        dt = time.perf_counter() - t0
+        h2d, d2h = fh.info("h2d_bytes_per_step"), fh.info("d2h_bytes_per_step")
+        if dist:
+            import torch
+            t = torch.tensor([dt], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+            b = torch.tensor([h2d, d2h], dtype=torch.int64)
+            dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            h2d, d2h = int(b[0]), int(b[1])
+        e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.e2e_steps * 1e3, "steps": args.e2e_steps,
+               "how": "fc_step_all on pinned host arrays: chunked H2D -> fused kernel -> D2H over 3 streams, wall clock with sync on both sides, max over ranks",
+               "check": chk}
+        fh.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_arm(args.workload, 3, 1, args.cpu_sample_cells or 4_000_000)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: %s" % (args.workload, desc), "cells_per_grid": n_total, "formula_set": fset,
+                       "surface_types": S, "bias": bias, "averaging": avg, "diagnostics": diag,
+                       "parallelism": "contiguous range per GPU (fc_shard_range), %d rank(s)" % world,
+                       "l2": "inputs exceed L2 (%.0f MB per step per GPU vs 126 MB), no flush" % (bytes_per_cell * max_size / 1e6)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "parity": parity, "diagnostics_sample": diag_sample,
+        }
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

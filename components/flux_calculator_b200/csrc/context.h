@@ -1,0 +1,137 @@
+// context.h -- host-side state behind fc_context: the local_field registry, method strings,
+// bias corrections, send list, and the plans derived from them.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/fluxcalc.h"
+#include "plan.h"
+
+struct fc_context;
+
+namespace fc {
+
+struct Buffer {
+    double *user = nullptr;      // pointer the host bound (host or device memory)
+    double *dev = nullptr;       // device pointer the kernels use (== user for device memory)
+    int64_t n = 0;
+    int grid = 0;
+    bool user_is_device = false;
+    bool user_is_pinned = false;
+    bool registered = false;     // we called cudaHostRegister on it
+    int refs = 0;
+};
+
+// host-side op: device pointers are resolved from buffer ids at launch time
+struct HOp {
+    int code = 0;
+    double cst = 0.0;
+    int grid = 1;
+    int out = -1, out2 = -1;     // buffer ids (-1: none)
+    int in[8] = {-1, -1, -1, -1, -1, -1, -1, -1};
+    int n_in = 0;
+    bool in0_is_bias = false;    // in[0] is the month slab of the corrections
+};
+
+struct OutputField {
+    int surface_type, grid, idx;
+    bool early;
+};
+
+struct RegridMatrix {
+    bool set = false;
+    int64_t nnz = 0, n_dst = 0, n_src = 0;
+    int64_t *row_ptr = nullptr;  // device, n_dst+1
+    int32_t *src_idx = nullptr;  // device, 0-based, grouped by destination in original element order
+    double *weight = nullptr;    // device
+};
+
+enum Quantity { Q_QSUR_T = 0, Q_QSUR_U, Q_QSUR_V, Q_MEVA, Q_HLAT, Q_HSEN, Q_MOM, Q_RBBR, Q_COUNT };
+
+struct FusedBundle {
+    bool ok = false;
+    FusedPlan plan;
+    std::vector<int> in_bufs, out_bufs;   // buffers to upload / download in host-pointer mode
+    std::vector<HOp> extra;               // averaging of pass-through variables (run after the fused launch)
+    // diagnostics slot -> (surface type, grid, var) of the active slots, compact order
+    std::vector<int> diag_slots;
+};
+
+extern thread_local std::string g_last_error;
+int fail(fc_context *ctx, int code, const char *fmt, ...);
+int classify_pointer(const void *p, bool *is_device, bool *is_pinned, int *device);
+int diag_fetch(fc_context *c);
+
+}  // namespace fc
+
+#define CUDA_TRY(ctx, call)                                                                                  \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fc::fail(ctx, FC_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e_), __FILE__, \
+                            __LINE__, #call);                                                                \
+    } while (0)
+
+struct fc_context {
+    int device = 0;
+    int S = 1;
+    int64_t n[4] = {0, 0, 0, 0};
+    cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pipe_done[3] = {nullptr, nullptr, nullptr};
+
+    std::vector<fc::Buffer> bufs;
+    int slot[FC_MAX_SURFACE_TYPES + 1][4][FC_MAX_VARNAMES + 1];
+    int method[fc::Q_COUNT][FC_MAX_SURFACE_TYPES + 1];
+    int dist_sw = -1;            // -1 auto, 0 off, 1 on
+
+    // bias corrections, month-major [12][n_t] on the device
+    double *corr_dev = nullptr;
+    bool corr_enabled = false;
+    int init_date = 19000101;
+    double *area_dev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool area_owned[4] = {false, false, false, false};
+
+    std::vector<fc::OutputField> outputs;
+    int64_t time = 0;
+
+    // options
+    bool force_generic = false;
+    bool pin_host = false;
+    bool diagnostics = false;
+    int h2d_chunks = 0;          // 0 = auto
+
+    // derived
+    bool dirty = true;
+    bool strict = false;
+    fc::Consts consts;
+    fc::FusedBundle fused[3];    // 0 early, 1 normal, 2 all
+    int fused_month = 0;         // month the bias pointer in the fused plans refers to
+
+    // diagnostics storage
+    double *diag_partials = nullptr;
+    size_t diag_partials_cap = 0;
+    double *diag_dev = nullptr;          // [kDiagSlots][3] compact
+    double *diag_host = nullptr;         // pinned copy, expanded to [kDiagSlots][3]
+    std::vector<int> diag_active;        // slot ids in compact order (of the last step)
+    bool diag_valid = false;
+
+    // NCCL
+    void *nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    fc::RegridMatrix regrid[4];
+
+    // live timing of the fused kernel (option "profile_kernel"): event pairs around each launch
+    bool profile_kernel = false;
+    std::vector<cudaEvent_t> prof_ev;    // start/stop pairs, recycled
+    size_t prof_used = 0;
+    cudaEvent_t user_ev[2] = {nullptr, nullptr};
+
+    int64_t launches = 0;
+    int64_t h2d_bytes = 0, d2h_bytes = 0;   // of the last step call
+    std::string err;
+};

@@ -1,0 +1,141 @@
+// plan.h -- launch plans shared by the host-side plan builder and the kernels.
+//
+// Two kinds of plan are built from the context (bound fields + method strings):
+//   * OpList    : the reference's pass sequence (flux_calculator_calculate.F90) as a list of per-cell
+//                 ops on device pointers.  Executed by the op-list interpreter kernel.  Exact reference
+//                 semantics for every configuration, including pointer aliasing ('copy', uniform
+//                 outputs) because each op reads/writes global memory in the reference's order.
+//   * FusedPlan : the same work for "canonical" configurations (no aliased outputs) as ONE pass over
+//                 SoA fields with every intermediate in registers.
+#pragma once
+
+#include <stdint.h>
+
+#include "formulas.cuh"
+
+namespace fc {
+
+enum Method : int {
+    M_NONE = 0,
+    M_ZERO,
+    M_COPY,
+    M_CCLM,
+    M_MOM5,
+    M_RCO,
+    M_WATER,
+    M_ICE,
+    M_STBO,
+    M_INVALID = -1
+};
+
+constexpr int kMaxSurfaceTypes = 10;
+constexpr int kMaxVars = 35;
+
+// ---------------------------------------------------------------------------------------------
+// op-list interpreter
+// ---------------------------------------------------------------------------------------------
+enum OpCode : int {
+    OP_ZERO = 0,      // out = 0.0
+    OP_COPY,          // out = in0                                     (distribute_radiation_flux)
+    OP_QSUR_CCLM,     // out = q_s(in0=FICE, in1=PSUR, in2=TSUR)
+    OP_MEVA_CCLM,     // out = evap(in0=a, in1=PSUR, in2=QATM, in3=QSUR, in4=T, in5=U, in6=V)
+    OP_MEVA_RCO,      // out = evap(in0=QATM, in1=TSUR, in2=U, in3=V)
+    OP_ADD,           // out = out + in0                               (bias correction)
+    OP_SCALE,         // out = in0 * cst                               (latent heat)
+    OP_HSEN_CCLM,     // out = hsen(in0=a, in1=PATM, in2=PSUR, in3=q, in4=TATM, in5=TSUR, in6=U, in7=V)
+    OP_HSEN_RCO,      // out = hsen(in0=TATM, in1=TSUR, in2=U, in3=V)
+    OP_MOM_CCLM,      // out/out2 = tau(in0=a, in1=PSUR, in2=QSUR, in3=TSUR, in4=U, in5=V)
+    OP_MOM_RCO,       // out/out2 = tau(in0=U, in1=V)
+    OP_RBBR,          // out = cst * in0**4
+    OP_MULADD         // out = out + in0*in1                           (average_across_surface_types)
+};
+
+struct Op {
+    int code;
+    int pad;
+    double cst;
+    double *out;
+    double *out2;          // second result of the momentum routines (north), may be null
+    const double *in[8];
+};
+
+constexpr int kMaxOps = 160;   // 10 types x (<=9 calculators + bias) + averaging of a few fields
+
+struct OpList {
+    int n;
+    int pad;
+    Op ops[kMaxOps];
+};
+
+// ---------------------------------------------------------------------------------------------
+// fused plan
+// ---------------------------------------------------------------------------------------------
+struct FusedTType {     // one surface type on the t grid
+    const double *fice, *psur, *tsur, *qatm, *tatm, *patm, *uatm, *vatm;
+    const double *a_evap;    // AMOI (CCLM) or CMOI (MOM5)
+    const double *a_sens;    // AMOI (CCLM) or CHEA (MOM5)
+    const double *qsur_in;   // QSUR when it is an input (method 'none' but bound)
+    const double *fare;
+    double *qsur, *meva, *hlat, *hsen, *rbbr, *rsdr;
+    int m_qsur, m_meva, m_hlat, m_hsen, m_rbbr, pad;
+    double latent_heat;      // L_v (water) or L_s (ice)
+};
+
+struct FusedUVType {    // one surface type on the u or v grid
+    const double *fice, *psur, *tsur, *a_mom, *uatm, *vatm, *qsur_in, *fare;
+    double *qsur, *mom;      // mom = UMOM on the u grid, VMOM on the v grid
+    int m_qsur, m_mom;
+};
+
+struct FusedT {
+    int64_t n;
+    const double *rsdd;      // RSDD of surface type 0 (null: no shortwave distribution)
+    const double *bias;      // corrections[month-1][0..n) or null
+    const double *area;      // cell areas (diagnostics) or null
+    // type-0 area-fraction averages (null = not averaged)
+    double *avg_qsur, *avg_meva, *avg_hlat, *avg_hsen, *avg_rbbr, *avg_rsdr;
+    FusedTType ty[kMaxSurfaceTypes];
+};
+
+struct FusedUV {
+    int64_t n;
+    int north;               // 0: east component (u grid), 1: north component (v grid)
+    int pad;
+    const double *area;
+    double *avg_qsur, *avg_mom;
+    FusedUVType ty[kMaxSurfaceTypes];
+};
+
+struct FusedPlan {
+    int S;                   // num_surface_types
+    int do_early;            // RBBR (+ its average) in this launch
+    int do_normal;           // everything else
+    int diag;                // accumulate diagnostics
+    int64_t cell0[3];        // first cell of this launch on each grid (chunked host pipeline)
+    int64_t cells[3];        // number of cells of this launch on each grid
+    Consts c;
+    FusedT t;
+    FusedUV uv[2];           // [0] = u grid, [1] = v grid
+    double *diag_partials;   // [blocks][diag_n][3]
+    int diag_n;              // number of active diagnostics slots
+    signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index (valid for active slots)
+};
+
+// diagnostics slot layout: slot(type 0..10, quantity)
+enum DiagQuantity { DQ_QSUR_T = 0, DQ_MEVA, DQ_HLAT, DQ_HSEN, DQ_RBBR, DQ_RSDR, DQ_QSUR_U, DQ_UMOM, DQ_QSUR_V, DQ_VMOM, DQ_COUNT };
+constexpr int kDiagSlots = (kMaxSurfaceTypes + 1) * DQ_COUNT;
+
+constexpr int kFusedThreads = 256;
+constexpr int kFusedVec = 2;                                  // cells per thread (128-bit accesses)
+constexpr int kFusedCellsPerBlock = kFusedThreads * kFusedVec;
+
+// launchers (kernels.cu)
+int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t stream);
+int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
+int launch_diag_finalize(const double *partials, int nblocks, int nslots, double *diag_out, cudaStream_t stream);
+int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
+int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,
+                      double *dst, int64_t n_dst, cudaStream_t stream);
+int fused_grid_blocks(const FusedPlan &plan);
+
+}  // namespace fc

@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's `MODULE flux_calculator_calculate`
+(flux_calculator_calculate.F90:25-385) on top of the C ABI (include/fluxcalc.h).
+
+`FluxCalculator` plays the role of the reference's module state: local_field(0:10,3)%var(35)
+(flux_calculator.F90:159), the which_* method arrays of namelist /input/ (:99-107), the bias
+corrections (bias_corrections.F90:26-33) and the send list.  The nine calculators keep the reference's
+names and meaning; `step_early/step_normal/step_all` are the fused replacements of the inlined sequence
+in the time loop (flux_calculator.F90:902, :972-991).  All arithmetic happens in the CUDA library.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, check, FluxCalcError
+from .fields import IDX, VARNAMES, METHODS, var_index
+from .memory import DeviceArray
+
+
+class FluxCalculator:
+    def __init__(self, grid_size, num_surface_types=1, device=0):
+        gs = (C.c_int64 * 3)(*[int(x) for x in grid_size])
+        self._ctx = C.c_void_p()
+        check(lib.fc_create(C.byref(self._ctx), gs, int(num_surface_types), int(device)))
+        self.grid_size = tuple(int(x) for x in grid_size)
+        self.num_surface_types = int(num_surface_types)
+        self.device = int(device)
+        self._keep = {}       # (type, grid, idx) -> array object (keeps host memory alive, like the Fortran host)
+        self._misc = []
+
+    # ---- life cycle -------------------------------------------------------------------------
+    def close(self):
+        if self._ctx:
+            lib.fc_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        return check(rc, self._ctx)
+
+    # ---- registry ---------------------------------------------------------------------------
+    def bind_field(self, surface_type, grid, var, array):
+        """local_field(surface_type, grid)%var(idx_<var>)%field => array   (None: nullify)"""
+        idx = var_index(var)
+        if array is None:
+            self._check(lib.fc_bind_field(self._ctx, surface_type, grid, idx, None, 0))
+            self._keep.pop((surface_type, grid, idx), None)
+            return
+        if isinstance(array, DeviceArray):
+            ptr, n = array.ptr, array.n
+        else:
+            if not (isinstance(array, np.ndarray) and array.dtype == np.float64 and array.flags.c_contiguous):
+                raise TypeError("fields must be contiguous float64 NumPy arrays or DeviceArrays")
+            ptr, n = array.ctypes.data, array.size
+        self._check(lib.fc_bind_field(self._ctx, surface_type, grid, idx, ptr, n))
+        self._keep[(surface_type, grid, idx)] = array
+
+    def field(self, surface_type, grid, var):
+        return self._keep.get((surface_type, grid, var_index(var)))
+
+    def set_method(self, which, surface_type, method):
+        self._check(lib.fc_set_method(self._ctx, which.encode(), surface_type, method.encode()))
+
+    def set_distribute_shortwave(self, on):
+        self._check(lib.fc_set_distribute_shortwave(self._ctx, -1 if on is None else int(bool(on))))
+
+    def set_corrections(self, corrections, enabled=True, init_date=19610101):
+        """corrections: Fortran array corrections(1,12,n) flattened in Fortran order, i.e. shape (n,12) C-order,
+        NumPy or DeviceArray (bias_corrections.F90:29-30,191)"""
+        if corrections is None:
+            self._check(lib.fc_set_corrections(self._ctx, 1, None, 0, 0, int(init_date)))
+            return
+        if isinstance(corrections, DeviceArray):
+            ptr, n = corrections.ptr, corrections.n // 12
+        else:
+            corrections = np.ascontiguousarray(corrections, dtype=np.float64)
+            ptr, n = corrections.ctypes.data, corrections.size // 12
+        self._misc.append(corrections)
+        self._check(lib.fc_set_corrections(self._ctx, 1, ptr, n, int(bool(enabled)), int(init_date)))
+
+    def add_output_field(self, surface_type, grid, var):
+        self._check(lib.fc_add_output_field(self._ctx, surface_type, grid, var_index(var)))
+
+    def set_area(self, grid, area):
+        if isinstance(area, DeviceArray):
+            ptr, n = area.ptr, area.n
+        else:
+            area = np.ascontiguousarray(area, dtype=np.float64)
+            ptr, n = area.ctypes.data, area.size
+        self._misc.append(area)
+        self._check(lib.fc_set_area(self._ctx, grid, ptr, n))
+
+    def set_time(self, seconds):
+        self._check(lib.fc_set_time(self._ctx, int(seconds)))
+
+    def set_option(self, name, value):
+        self._check(lib.fc_set_option(self._ctx, name.encode(), int(value)))
+
+    def info(self, name):
+        return int(lib.fc_get_info(self._ctx, name.encode()))
+
+    def prepare(self, strict=False):
+        self._check(lib.fc_prepare(self._ctx, int(bool(strict))))
+
+    # ---- the nine calculators (same names as the reference) ---------------------------------
+    def calc_spec_vapor_surface(self, which_grid):
+        self._check(lib.fc_calc_spec_vapor_surface(self._ctx, which_grid))
+
+    def calc_flux_mass_evap(self):
+        self._check(lib.fc_calc_flux_mass_evap(self._ctx))
+
+    def calc_flux_heat_latent(self):
+        self._check(lib.fc_calc_flux_heat_latent(self._ctx))
+
+    def calc_flux_heat_sensible(self):
+        self._check(lib.fc_calc_flux_heat_sensible(self._ctx))
+
+    def calc_flux_momentum_east(self, which_grid=2):
+        self._check(lib.fc_calc_flux_momentum_east(self._ctx, which_grid))
+
+    def calc_flux_momentum_north(self, which_grid=3):
+        self._check(lib.fc_calc_flux_momentum_north(self._ctx, which_grid))
+
+    def calc_flux_radiation_blackbody(self):
+        self._check(lib.fc_calc_flux_radiation_blackbody(self._ctx))
+
+    def distribute_shortwave_radiation_flux(self):
+        self._check(lib.fc_distribute_shortwave_radiation_flux(self._ctx))
+
+    def average_across_surface_types(self, which_grid, var):
+        self._check(lib.fc_average_across_surface_types(self._ctx, which_grid, var_index(var)))
+
+    # ---- fused phases -------------------------------------------------------------------------
+    def step_early(self, current_step_time=0):
+        self._check(lib.fc_step_early(self._ctx, int(current_step_time)))
+
+    def step_normal(self, current_step_time=0):
+        self._check(lib.fc_step_normal(self._ctx, int(current_step_time)))
+
+    def step_all(self, current_step_time=0):
+        self._check(lib.fc_step_all(self._ctx, int(current_step_time)))
+
+    def run_steps(self, t0, timestep, nsteps):
+        self._check(lib.fc_run_steps(self._ctx, int(t0), int(timestep), int(nsteps)))
+
+    def synchronize(self):
+        self._check(lib.fc_synchronize(self._ctx))
+
+    def event_record(self, which):
+        self._check(lib.fc_event_record(self._ctx, int(which)))
+
+    def event_elapsed_ms(self):
+        ms = C.c_double()
+        self._check(lib.fc_event_elapsed_ms(self._ctx, C.byref(ms)))
+        return ms.value
+
+    def kernel_time_ms(self):
+        ms, cnt = C.c_double(), C.c_int64()
+        self._check(lib.fc_kernel_time_ms(self._ctx, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
+
+    @property
+    def stream(self):
+        return lib.fc_get_stream(self._ctx)
+
+    # ---- diagnostics / multi-GPU -------------------------------------------------------------
+    def diagnostics(self, surface_type, grid, var):
+        out = (C.c_double * 3)()
+        self._check(lib.fc_get_diagnostics(self._ctx, surface_type, grid, var_index(var), out))
+        return tuple(out)
+
+    def comm_init(self, unique_id, rank, nranks):
+        self._check(lib.fc_comm_init(self._ctx, unique_id, rank, nranks))
+
+    def allreduce_diagnostics(self):
+        self._check(lib.fc_allreduce_diagnostics(self._ctx))
+
+    # ---- regridding ("next" row) ---------------------------------------------------------------
+    def set_regrid_matrix(self, direction, src_index, dst_index, weight):
+        s = np.ascontiguousarray(src_index, dtype=np.int32)
+        d = np.ascontiguousarray(dst_index, dtype=np.int32)
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        self._check(lib.fc_set_regrid_matrix(self._ctx, direction, s.size, s.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             d.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             w.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def regrid(self, direction, dst, src):
+        dp = dst.ptr if isinstance(dst, DeviceArray) else dst.ctypes.data
+        sp = src.ptr if isinstance(src, DeviceArray) else src.ctypes.data
+        self._check(lib.fc_regrid(self._ctx, direction, dp, sp))
+
+
+def comm_get_unique_id():
+    buf = C.create_string_buffer(128)
+    check(lib.fc_comm_get_unique_id(buf))
+    return buf.raw
+
+
+def current_month(init_date, seconds):
+    """pyfort/datetime_helpers.py:4-13 replacement"""
+    return int(lib.fc_current_month(int(init_date), int(seconds)))
+
+
+def shard_range(n, rank, nranks, align=32):
+    off, size = C.c_int64(), C.c_int64()
+    check(lib.fc_shard_range(int(n), int(rank), int(nranks), int(align), C.byref(off), C.byref(size)))
+    return off.value, size.value

@@ -1,0 +1,152 @@
+"""-m gpu: the fused / generic per-step path through the C ABI against the CPU oracle on seeded fields."""
+import numpy as np
+import pytest
+
+from oracle_py import Oracle, ulp_diff
+from tolerances import check_field
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chunks=None, diagnostics=False):
+    from components.flux_calculator_b200 import DeviceArray
+    # oracle
+    o_in, o_out = sc.clone()
+    orc = Oracle(sc.n, sc.S)
+    sc.apply(orc, o_in, o_out)
+    if phases == "all":
+        orc.step_all(t)
+    else:
+        orc.step_early(t)
+        orc.step_normal(t)
+    # CUDA
+    g_in, g_out = sc.clone()
+    fc = fcmod.FluxCalculator(sc.n, sc.S)
+    if force_generic:
+        fc.set_option("force_generic", 1)
+    if chunks:
+        fc.set_option("h2d_chunks", chunks)
+    if mode == "host":
+        sc.apply(fc, g_in, g_out)
+        wrapped = None
+    else:
+        wrapped = sc.apply(fc, g_in, g_out, wrap=lambda a: DeviceArray.from_numpy(a))
+    if diagnostics:
+        for g in (1, 2, 3):
+            fc.set_area(g, sc.area[g])
+        fc.set_option("diagnostics", 1)
+    fc.prepare()
+    if phases == "all":
+        fc.step_all(t)
+    else:
+        fc.step_early(t)
+        fc.step_normal(t)
+    fc.synchronize()
+    if wrapped is not None:
+        for d in (g_in, g_out):
+            for k, a in d.items():
+                wrapped[id(a)].download(a)
+    return fc, o_out, g_out, o_in, g_in
+
+
+def compare(sc, o_out, g_out):
+    worst = {}
+    for k in sorted(o_out):
+        name = k[2]
+        worst[k] = check_field(name, g_out[k], o_out[k], sc.formula_set)
+    return worst
+
+
+@pytest.mark.parametrize("fset", ["CCLM", "MOM5", "RCO"])
+@pytest.mark.parametrize("mode", ["host", "device"])
+def test_step_all_s1(fcmod, fset, mode):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario(fset, n=(20000, 20000, 20000), S=1, bias=(fset == "MOM5"))
+    fc, o_out, g_out, o_in, g_in = run_both(fcmod, sc, mode)
+    assert fc.info("fused") == 1
+    compare(sc, o_out, g_out)
+    for k in o_in:      # inputs untouched
+        assert np.array_equal(o_in[k], g_in[k], equal_nan=True)
+
+
+@pytest.mark.parametrize("fset", ["CCLM", "MOM5", "RCO"])
+def test_generic_path_matches(fcmod, fset):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario(fset, n=(5003, 4999, 5001), S=2, bias=True, averaging=True)
+    fc, o_out, g_out, _, _ = run_both(fcmod, sc, "host", force_generic=True)
+    assert fc.info("fused") == 0
+    compare(sc, o_out, g_out)
+    fc2, _, f_out, _, _ = run_both(fcmod, sc, "device")
+    assert fc2.info("fused") == 1
+    for k in g_out:     # fused and generic kernels agree bit for bit
+        assert np.array_equal(g_out[k], f_out[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("S", [2, 3, 5])
+def test_surface_types_and_averaging(fcmod, S):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(7001, 7003, 6999), S=S, bias=True, averaging=True)
+    for mode in ("host", "device"):
+        fc, o_out, g_out, _, _ = run_both(fcmod, sc, mode, t=40 * 86400)
+        assert fc.info("fused") == 1
+        compare(sc, o_out, g_out)
+    # averaging itself is exact arithmetic on the per-type values
+    for (i, g, name) in sc.send:
+        acc = np.zeros(sc.n[g - 1])
+        for t in range(1, S + 1):
+            acc = acc + g_out[(t, g, name)] * sc.inputs[(t, g, "FARE")]
+        assert np.array_equal(acc, g_out[(0, g, name)])
+
+
+def test_split_phases_equal_fused_all(fcmod):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(4096, 4096, 4096), S=2, bias=True, averaging=True, passthrough_avg=True)
+    _, o_out, a_out, _, _ = run_both(fcmod, sc, "device", phases="all")
+    _, _, s_out, _, _ = run_both(fcmod, sc, "device", phases="split")
+    compare(sc, o_out, a_out)
+    for k in a_out:
+        assert np.array_equal(a_out[k], s_out[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("n", [(0, 0, 0), (1, 1, 1), (3, 2, 1), (511, 513, 1025), (33, 0, 7)])
+def test_ragged_and_tiny_grids(fcmod, n):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=n, S=1, bias=True)
+    for mode in ("host", "device"):
+        _, o_out, g_out, _, _ = run_both(fcmod, sc, mode)
+        compare(sc, o_out, g_out)
+
+
+def test_month_rollover_bias(fcmod):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("MOM5", n=(3000, 3000, 3000), S=1, bias=True, init_date=19611231)
+    outs = []
+    for t in (0, 86399, 86400, 31 * 86400 + 86400):     # Dec, Dec, Jan, Feb
+        _, o_out, g_out, _, _ = run_both(fcmod, sc, "host", t=t)
+        compare(sc, o_out, g_out)
+        outs.append(g_out[(1, 1, "MEVA")].copy())
+    assert np.array_equal(outs[0], outs[1])
+    assert not np.array_equal(outs[1], outs[2])
+    assert not np.array_equal(outs[2], outs[3])
+
+
+def test_chunked_host_pipeline(fcmod):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(300001, 299999, 300003), S=1, bias=True)
+    _, o_out, g1, _, _ = run_both(fcmod, sc, "host", chunks=1)
+    _, _, g7, _, _ = run_both(fcmod, sc, "host", chunks=7)
+    compare(sc, o_out, g1)
+    for k in g1:
+        assert np.array_equal(g1[k], g7[k], equal_nan=True), k
+
+
+def test_diagnostics(fcmod):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(10007, 10009, 10011), S=2, bias=True, averaging=True)
+    fc, o_out, g_out, _, _ = run_both(fcmod, sc, "device", diagnostics=True)
+    compare(sc, o_out, g_out)
+    for (i, g, name), arr in g_out.items():
+        s, mn, mx = fc.diagnostics(i, g, name)
+        assert mn == arr.min() and mx == arr.max(), (i, g, name)
+        ref = float(np.sum(sc.area[g] * arr))
+        assert abs(s - ref) <= 1e-11 * float(np.sum(np.abs(sc.area[g] * arr))), (i, g, name)
