@@ -1,0 +1,115 @@
+"""not-gpu: the C-ABI library loads and exports every symbol include/fluxcalc.h declares; the pure host
+entry points (no device needed) behave; compute entry points fail LOUDLY without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fluxcalc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fc_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported_and_bound(fcmod):
+    syms = declared_symbols()
+    assert len(syms) >= 60
+    for s in syms:
+        assert hasattr(fcmod.lib, s), "libfluxcalc_b200.so does not export " + s
+    assert sorted(fcmod.SIGNATURES) == syms, "ctypes table and header disagree"
+
+
+def test_header_mirrors_the_14_flux_library_routines(golden):
+    syms = set(declared_symbols())
+    for routine in golden["routine_signatures"]:
+        name = "fc_" + routine.replace("stbo", "StBo")
+        assert name in syms, name
+
+
+def test_header_mirrors_the_9_calculators():
+    ref = open(os.path.join(ROOT, "tests", "golden", "flux_lib_golden.json")).read()
+    syms = set(declared_symbols())
+    for calc in ("calc_spec_vapor_surface", "calc_flux_mass_evap", "calc_flux_heat_latent", "calc_flux_heat_sensible",
+                 "calc_flux_momentum_east", "calc_flux_momentum_north", "calc_flux_radiation_blackbody",
+                 "distribute_shortwave_radiation_flux", "average_across_surface_types"):
+        assert "fc_" + calc in syms
+        if calc != "average_across_surface_types":
+            assert calc in ref      # the name was found in the reference's time loop / calculate module
+
+
+def test_variable_table_matches_reference_order(fcmod):
+    names = ("ALBE ALBA AMOI AMOM FARE FICE PATM PSUR QATM TATM TSUR UATM VATM U10M V10M CMOM CMOI CHEA QSUR HLAT HSEN "
+             "MEVA MPRE MRAI MSNO RBBR RLWD RLWU RSID RSIU RSIN RSDD RSDR UMOM VMOM").split()   # basic.F90:43-51
+    assert fcmod.VARNAMES == names
+    for i, n in enumerate(names, 1):
+        assert fcmod.lib.fc_var_index(n.encode()) == i
+        assert fcmod.lib.fc_var_name(i).decode() == n
+    assert fcmod.lib.fc_var_index(b"XXXX") == 0
+
+
+def test_month_function_matches_python_datetime(fcmod):
+    from datetime import datetime, timedelta
+    rng = np.random.default_rng(11)
+    for _ in range(3000):
+        y, mo, d = int(rng.integers(1850, 2200)), int(rng.integers(1, 13)), int(rng.integers(1, 29))
+        secs = int(rng.integers(0, 200 * 365 * 86400))
+        init = y * 10000 + mo * 100 + d
+        ref = (datetime.strptime(str(init), "%Y%m%d") + timedelta(seconds=secs)).month
+        assert fcmod.current_month(init, secs) == ref
+    for (d, s), m in (((20000101, 0), 1), ((20000201, 29 * 86400), 3), ((19000201, 28 * 86400), 3),
+                      ((19991231, 86399), 12), ((19991231, 86400), 1)):
+        assert fcmod.current_month(d, s) == m
+    assert fcmod.current_month(20001301, 0) == 0       # not a date
+
+
+def test_shard_range_is_a_partition(fcmod):
+    for n in (0, 1, 31, 512, 20_000, 1_000_003, 10**7):
+        for R in (1, 2, 3, 4, 8):
+            end = 0
+            for r in range(R):
+                off, size = fcmod.shard_range(n, r, R, 512)
+                assert off == end and size >= 0
+                assert off % 512 == 0                  # every shard start keeps 256-byte alignment
+                end = off + size
+            assert end == n
+    with pytest.raises(fcmod.FluxCalcError):
+        fcmod.shard_range(10, 4, 4 - 1)
+
+
+def test_shard_range_reduces_to_decomp_def_apple_rule(fcmod):
+    import oracle_py
+    lib = oracle_py.load()
+    for n, R in ((1000, 4), (10**7, 8), (77, 5)):
+        for r in range(R):
+            off, size = C.c_int64(), C.c_int64()
+            lib.orc_decomp_apple(n, r, R, C.byref(off), C.byref(size))
+            assert fcmod.shard_range(n, r, R, 1) == (off.value, size.value)     # decomp_def.F90:14-31
+
+
+def test_no_cpu_fallback(fcmod):
+    """on a box without a GPU every compute entry point must fail with FC_ERR_CUDA, never compute on the host"""
+    if fcmod.lib.fc_device_count() > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(fcmod.FluxCalcError) as e:
+        fcmod.FluxCalculator((8, 8, 8), 1)
+    assert e.value.code == 4 and "no CPU fallback" in e.value.message
+    out = np.full(4, np.nan)
+    with pytest.raises(fcmod.FluxCalcError) as e:
+        fcmod.flux_library.flux_radiation_blackbody_StBo(out, np.full(4, 280.0))
+    assert e.value.code == 4
+    assert np.isnan(out).all()
+
+
+def test_product_never_references_the_oracle():
+    """the package and its C/CUDA sources must not include, import or link anything under oracle/"""
+    pkg = os.path.join(ROOT, "components")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".F90", "Makefile")):
+                text = open(os.path.join(dp, fn), errors="replace").read()
+                assert "oracle_py" not in text and "flux_oracle" not in text and "liboracle" not in text, os.path.join(dp, fn)
