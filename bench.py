@@ -178,6 +178,9 @@ def main():
     ap.add_argument("--cpu-sample-cells", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--diag", type=int, default=None, help="override the workload's diagnostics switch (0/1)")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance in blocks (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -202,6 +205,8 @@ def main():
     fset, n_total, S, bias, avg, diag, desc = WORKLOADS[args.workload]
     if args.cells:
         n_total = args.cells
+    if args.diag is not None:
+        diag = bool(args.diag)
     off, size = m.shard_range(n_total, rank, world, 512)
     sc = build_scenario(args.workload, (off, size), cells=n_total)
 
@@ -213,6 +218,8 @@ def main():
         for g in (1, 2, 3):
             fc.set_area(g, sc.area[g])
         fc.set_option("diagnostics", 1)
+    if args.prefetch is not None:
+        fc.set_option("prefetch_distance", args.prefetch)
     fc.prepare()
     assert fc.info("fused") == 1, "bench workload must run on the fused kernel"
     if world > 1 and diag:
@@ -281,7 +288,7 @@ def main():
 
     # parity spot check of what was just timed (first 4096 cells of every output vs the oracle)
     parity = None
-    if rank == 0:
+    if rank == 0 and not args.no_parity:
         from oracle_py import Oracle
         from tolerances import check_field
         ns = min(4096, size)

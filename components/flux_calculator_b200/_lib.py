@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfluxcalc_b200.so")
+LIB_PATH = os.environ.get("FLUXCALC_LIB") or os.path.join(_HERE, "libfluxcalc_b200.so")   # env: tuning builds only
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(

@@ -460,7 +460,8 @@ extern "C" int fc_set_option(fc_context *c, const char *name, int64_t value)
     if (!strcmp(name, "force_generic")) c->force_generic = value != 0;
     else if (!strcmp(name, "pin_host")) c->pin_host = value != 0;
     else if (!strcmp(name, "h2d_chunks")) c->h2d_chunks = (int)std::max<int64_t>(0, std::min<int64_t>(value, 256));
-    else if (!strcmp(name, "diagnostics")) c->diagnostics = value != 0;
+    else if (!strcmp(name, "diagnostics")) c->diagnostics = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
+    else if (!strcmp(name, "prefetch_distance")) c->prefetch_distance = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else if (!strcmp(name, "profile_kernel")) {
         c->profile_kernel = value != 0;
         c->prof_used = 0;
@@ -1087,14 +1088,16 @@ static bool build_fused(fc_context *c, bool do_early, bool do_normal, FusedBundl
 
     // diagnostics slots
     P.diag = 0;
+    memset(P.diag_map, 0xff, sizeof P.diag_map);
+    P.prefetch_distance = c->prefetch_distance;
     if (c->diagnostics) {
         for (int g = 1; g <= 3; ++g)
             if ((g == 1 || do_normal) && !c->area_dev[g] && c->n[g] > 0) return false;   // reported by prepare
         P.t.area = c->area_dev[1];
         P.uv[0].area = c->area_dev[2];
         P.uv[1].area = c->area_dev[3];
-        P.diag = 1;
-        memset(P.diag_map, 0, sizeof P.diag_map);
+        P.diag = c->diagnostics;
+        memset(P.diag_map, 0xff, sizeof P.diag_map);
         auto act = [&](int type, int q) {
             const int s = type * DQ_COUNT + q;
             P.diag_map[s] = (signed char)F.diag_slots.size();
@@ -1248,9 +1251,12 @@ extern "C" int fc_average_across_surface_types(fc_context *c, int g, int idx)
 // ---------------------------------------------------------------------------------------------
 // fused steps
 // ---------------------------------------------------------------------------------------------
-static int ensure_diag_storage(fc_context *c, const FusedPlan &P, int total_blocks)
+static int ensure_diag_storage(fc_context *c, FusedPlan &P)
 {
-    const size_t need = (size_t)total_blocks * P.diag_n * 3 * sizeof(double);
+    const int64_t rows = fused_diag_rows(P);
+    const int planes = P.diag >= 2 ? 3 : 1;
+    const size_t need = (size_t)planes * P.diag_n * (size_t)rows * sizeof(double) +
+                        (size_t)diag_tmp_doubles(rows, P.diag_n) * sizeof(double);
     if (need > c->diag_partials_cap) {
         cudaFree(c->diag_partials);
         c->diag_partials = nullptr;
@@ -1259,7 +1265,15 @@ static int ensure_diag_storage(fc_context *c, const FusedPlan &P, int total_bloc
     }
     if (!c->diag_dev) CUDA_TRY(c, cudaMalloc(&c->diag_dev, sizeof(double) * kDiagSlots * 3));
     if (!c->diag_host) CUDA_TRY(c, cudaHostAlloc(&c->diag_host, sizeof(double) * kDiagSlots * 3 * 2, cudaHostAllocDefault));
+    P.diag_partials = c->diag_partials;
+    P.diag_rows = rows;
     return FC_OK;
+}
+
+static double *diag_tmp(fc_context *c, const FusedPlan &P)
+{
+    const int planes = P.diag >= 2 ? 3 : 1;
+    return c->diag_partials + (size_t)planes * P.diag_n * (size_t)P.diag_rows;
 }
 
 static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
@@ -1276,11 +1290,8 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     int nlaunch = 0;
 
     if (!any_host) {
-        if (P.diag) {
-            const int nb = fused_grid_blocks(P);
-            if (int rc = ensure_diag_storage(c, P, nb)) return rc;
-            P.diag_partials = c->diag_partials;
-        }
+        if (P.diag)
+            if (int rc = ensure_diag_storage(c, P)) return rc;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->profile_kernel && c->prof_used < 8192) {
             while (c->prof_ev.size() < c->prof_used + 2) {
@@ -1297,11 +1308,13 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         if (e1) CUDA_TRY(c, cudaEventRecord(e1, c->stream));
         c->launches += nlaunch;
         if (P.diag) {
-            if (launch_diag_finalize(c->diag_partials, fused_grid_blocks(P), P.diag_n, c->diag_dev, c->stream))
+            int nl = 0;
+            if (launch_diag_finalize(P, diag_tmp(c, P), c->diag_dev, c->stream, &nl))
                 return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
-            c->launches++;
+            c->launches += nl;
             c->diag_active = F.diag_slots;
             c->diag_valid = false;
+            c->diag_level = P.diag;
         }
         if (!F.extra.empty())
             if (int rc = run_ops(c, F.extra)) return rc;
@@ -1313,11 +1326,8 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     int64_t nmax = std::max(c->n[1], std::max(c->n[2], c->n[3]));
     int K = c->h2d_chunks > 0 ? c->h2d_chunks : (int)std::min<int64_t>(16, std::max<int64_t>(1, nmax / 262144));
     if (P.diag) K = 1;   // keep the diagnostics partial layout simple
-    if (P.diag) {
-        const int nb = fused_grid_blocks(P);
-        if (int rc = ensure_diag_storage(c, P, nb)) return rc;
-        P.diag_partials = c->diag_partials;
-    }
+    if (P.diag)
+        if (int rc = ensure_diag_storage(c, P)) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < K; ++k) {
         cudaStream_t s = c->pipe[k % 3];
@@ -1352,11 +1362,13 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     c->launches += nlaunch;
     for (int k = 0; k < 3; ++k) CUDA_TRY(c, cudaStreamSynchronize(c->pipe[k]));
     if (P.diag) {
-        if (launch_diag_finalize(c->diag_partials, fused_grid_blocks(P), P.diag_n, c->diag_dev, c->stream))
+        int nl = 0;
+        if (launch_diag_finalize(P, diag_tmp(c, P), c->diag_dev, c->stream, &nl))
             return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
-        c->launches++;
+        c->launches += nl;
         c->diag_active = F.diag_slots;
         c->diag_valid = false;
+        c->diag_level = P.diag;
     }
     if (!F.extra.empty())
         if (int rc = run_ops(c, F.extra)) return rc;
@@ -1505,6 +1517,7 @@ extern "C" int fc_get_diagnostics(fc_context *c, int i, int g, int idx, double o
         return fail(c, FC_ERR_STATE, "fc_get_diagnostics: %s of surface_type %d was not computed by the last step", kVarNames[idx], i);
     if (int rc = diag_fetch(c)) return rc;
     for (int j = 0; j < 3; ++j) out[j] = c->diag_host[s * 3 + j];
+    if (c->diag_level < 2) out[1] = out[2] = nan("");   // min/max only at diagnostics level 2
     return FC_OK;
 }
 

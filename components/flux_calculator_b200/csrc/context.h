@@ -101,8 +101,9 @@ struct fc_context {
     // options
     bool force_generic = false;
     bool pin_host = false;
-    bool diagnostics = false;
+    int diagnostics = 0;         // 0 off, 1 area-weighted sums, 2 sums + min/max
     int h2d_chunks = 0;          // 0 = auto
+    int prefetch_distance = 0;   // L2 prefetch look-ahead of the fused kernel, in 512-cell blocks (0 = off)
 
     // derived
     bool dirty = true;
@@ -118,6 +119,7 @@ struct fc_context {
     double *diag_host = nullptr;         // pinned copy, expanded to [kDiagSlots][3]
     std::vector<int> diag_active;        // slot ids in compact order (of the last step)
     bool diag_valid = false;
+    int diag_level = 0;                  // level of the last step
 
     // NCCL
     void *nccl_comm = nullptr;

@@ -1,15 +1,14 @@
-// formulas.cuh -- per-cell flux formulae as __device__ inlines (binary64).
+// formulas.cuh -- the per-cell flux formulae, written ONCE as templates over an arithmetic policy
+// (vmath.cuh): ExactScalar for one cell with CUDA's IEEE routines, FastVec<V> for V cells in lock step.
 //
-// Each function follows one routine of the reference's flux_lib in the Fortran evaluation order
-// (left to right within equal precedence, parentheses as written).  Products and sums use the
-// *_rn intrinsics, which the compiler never contracts into FMA, so every +,-,*,/,sqrt is the same
-// IEEE-754 operation the reference's `-fp-model precise` build performs; only exp() and pow()
-// (CUDA libdevice: <=1 ulp / <=2 ulp) can differ from the host libm by a last-place unit.
-// Reference paths relative to /root/reference/src/flux_lib.
+// Each function follows one routine of the reference's flux_lib in the Fortran evaluation order (left to
+// right within equal precedence, parentheses as written).  The policies implement mul/add/sub with the
+// *_rn intrinsics (never contracted into FMA) and div/sqrt correctly rounded, so every +,-,*,/,sqrt is the
+// same IEEE-754 operation the reference's `-fp-model precise` build performs; only exp() and pow() can
+// differ from the host libm in the last place.  Reference paths relative to /root/reference/src/flux_lib.
 #pragma once
 
-#include <cuda_runtime.h>
-#include <math.h>
+#include "vmath.cuh"
 
 namespace fc {
 
@@ -48,96 +47,120 @@ __host__ __device__ inline Consts make_consts(double c_p = 1005.0, double L_v = 
     return c;
 }
 
-#define FC_DI __device__ __forceinline__
-
+// plain scalar helpers (averaging, diagnostics)
 FC_DI double mul(double a, double b) { return __dmul_rn(a, b); }
 FC_DI double add(double a, double b) { return __dadd_rn(a, b); }
-FC_DI double sub(double a, double b) { return __dsub_rn(a, b); }
-FC_DI double dvd(double a, double b) { return __ddiv_rn(a, b); }
 
 // vel = sqrt(u*u + v*v)   (e.g. mass/flux_mass_evap.F90:76)
-FC_DI double wind_speed(double u, double v) { return __dsqrt_rn(add(mul(u, u), mul(v, v))); }
+template <class M>
+FC_DI typename M::T wind_speed(M &m, const typename M::T &u, const typename M::T &v)
+{
+    return m.sqrt(M::add(M::mul(u, u), M::mul(v, v)));
+}
 
 // auxiliaries/flux_aux_vapor.F90:60-68
-FC_DI double spec_vapor_surface_cclm(double f_ice, double p_s, double T_s, const Consts &c)
+template <class M>
+FC_DI typename M::T spec_vapor_surface_cclm(M &m, const typename M::T &f_ice, const typename M::T &p_s,
+                                            const typename M::T &T_s, const Consts &c)
 {
     const double alpha_water = 17.2693882, alpha_ice = 21.8745584;      // :39-40
     const double T_1 = 273.16, T_2_water = 35.86, T_2_ice = 7.66;       // :41-44
     const double p_0 = 610.78;                                          // :45
-    const double alpha = add(alpha_water, mul(alpha_ice - alpha_water, f_ice));   // :60
-    const double T_2 = add(T_2_water, mul(T_2_ice - T_2_water, f_ice));           // :61
-    const double e_sat = mul(p_0, exp(dvd(mul(alpha, sub(T_s, T_1)), sub(T_s, T_2))));  // :63-64
-    return dvd(mul(c.rd_over_rv, e_sat), sub(p_s, mul(c.one_m_rd_rv, e_sat)));          // :66-68
+    const auto alpha = M::add(M::bc(alpha_water), M::mul(M::bc(alpha_ice - alpha_water), f_ice));   // :60
+    const auto T_2 = M::add(M::bc(T_2_water), M::mul(M::bc(T_2_ice - T_2_water), f_ice));           // :61
+    const auto arg = m.div(M::mul(alpha, M::sub(T_s, M::bc(T_1))), M::sub(T_s, T_2));
+    const auto e_sat = M::mul(M::bc(p_0), m.exp(arg));                                              // :63-64
+    return m.div(M::mul(M::bc(c.rd_over_rv), e_sat), M::sub(p_s, M::mul(M::bc(c.one_m_rd_rv), e_sat)));   // :66-68
 }
 
 // T_tilde = T * (1.0 + (R_v/R_d - 1.0) * q)    (mass/flux_mass_evap.F90:72-74 and siblings)
-FC_DI double t_tilde(double T, double q, const Consts &c) { return mul(T, add(1.0, mul(c.rv_over_rd_m1, q))); }
+template <class M>
+FC_DI typename M::T t_tilde(const typename M::T &T, const typename M::T &q, const Consts &c)
+{
+    return M::mul(T, M::add(M::bc(1.0), M::mul(M::bc(c.rv_over_rd_m1), q)));
+}
 
 // mass/flux_mass_evap.F90:72-83; `vel` passed in so the caller can share it with the sensible heat
-FC_DI double flux_mass_evap_cclm(double a_moisture, double p_s, double q_a, double q_s, double T_s, double vel,
-                                 const Consts &c)
+template <class M>
+FC_DI typename M::T flux_mass_evap_cclm(M &m, const typename M::T &a_moisture, const typename M::T &p_s,
+                                        const typename M::T &q_a, const typename M::T &q_s, const typename M::T &T_s,
+                                        const typename M::T &vel, const Consts &c)
 {
-    const double T_tilde = t_tilde(T_s, q_s, c);
-    const double flux_air = dvd(mul(mul(a_moisture, fmax(vel, c.u_min_evap)), p_s),
-                                mul(c.gas_constant_air, T_tilde));     // :78-80
-    return mul(flux_air, sub(q_s, q_a));                                // :82-83
+    const auto T_tilde = t_tilde<M>(T_s, q_s, c);
+    const auto flux_air = m.div(M::mul(M::mul(a_moisture, M::max(vel, M::bc(c.u_min_evap))), p_s),
+                                M::mul(M::bc(c.gas_constant_air), T_tilde));     // :78-80
+    return M::mul(flux_air, M::sub(q_s, q_a));                                    // :82-83
 }
 
 // mass/flux_mass_evap.F90:148-156 (Meier et al. 1999)
-FC_DI double flux_mass_evap_rco(double q_a, double T_s, double vel)
+template <class M>
+FC_DI typename M::T flux_mass_evap_rco(M &m, const typename M::T &q_a, const typename M::T &T_s,
+                                       const typename M::T &vel)
 {
     const double rho_a = 1.225, c_aw = 1.15E-03, epsilon = 0.62197, P_0 = 1.013E+05;   // :135-138
     const double r = 6.1078E+02, c_1 = 17.269, c_2 = 35.86;                            // :143-145
-    const double e_w = mul(r, exp(dvd(mul(c_1, sub(T_s, 273.15)), sub(T_s, c_2))));    // :148
-    const double q_w = dvd(mul(epsilon, e_w), P_0);                                    // :151
-    return mul(mul(rho_a * c_aw, vel), sub(q_w, q_a));                                 // :156
+    const auto e_w = M::mul(M::bc(r), m.exp(m.div(M::mul(M::bc(c_1), M::sub(T_s, M::bc(273.15))),
+                                                  M::sub(T_s, M::bc(c_2)))));          // :148
+    const auto q_w = m.div(M::mul(M::bc(epsilon), e_w), M::bc(P_0));                   // :151
+    return M::mul(M::mul(M::bc(rho_a * c_aw), vel), M::sub(q_w, q_a));                 // :156
 }
 
-// heat/flux_heat_latent.F90:41 (ice: L_s) and :65 (water: L_v)
-FC_DI double flux_heat_latent(double evap, double latent_heat) { return mul(evap, latent_heat); }
-
 // heat/flux_heat_sensible.F90:84-98
-FC_DI double flux_heat_sensible_cclm(double a_moisture, double p_a, double p_s, double q_s, double T_a, double T_s,
-                                     double vel, const Consts &c)
+template <class M>
+FC_DI typename M::T flux_heat_sensible_cclm(M &m, const typename M::T &a_moisture, const typename M::T &p_a,
+                                            const typename M::T &p_s, const typename M::T &q_s,
+                                            const typename M::T &T_a, const typename M::T &T_s,
+                                            const typename M::T &vel, const Consts &c)
 {
-    const double T_tilde = t_tilde(T_s, q_s, c);                        // :84-86
-    const double flux_air = dvd(mul(mul(a_moisture, fmax(vel, c.u_min_evap)), p_s),
-                                mul(c.gas_constant_air, T_tilde));     // :90-92
-    const double EF = pow(dvd(p_s, p_a), c.rd_over_cp);                 // :94-95
-    return mul(mul(flux_air, c.heat_capacity_air), sub(T_s, mul(T_a, EF)));   // :97-98
+    const auto T_tilde = t_tilde<M>(T_s, q_s, c);                                 // :84-86
+    const auto flux_air = m.div(M::mul(M::mul(a_moisture, M::max(vel, M::bc(c.u_min_evap))), p_s),
+                                M::mul(M::bc(c.gas_constant_air), T_tilde));     // :90-92
+    const auto EF = m.powc(m.div(p_s, p_a), c.rd_over_cp);                        // :94-95
+    return M::mul(M::mul(flux_air, M::bc(c.heat_capacity_air)), M::sub(T_s, M::mul(T_a, EF)));   // :97-98
 }
 
 // heat/flux_heat_sensible.F90:157-165
-FC_DI double flux_heat_sensible_rco(double T_a, double T_s, double vel)
+template <class M>
+FC_DI typename M::T flux_heat_sensible_rco(const typename M::T &T_a, const typename M::T &T_s,
+                                           const typename M::T &vel)
 {
-    const double rho_a = 1.225, c_pa = 1.008E+03;                       // :151-152
-    const double c_aw = (T_a < T_s) ? 1.13E-03 : 0.66E-03;              // :157-161
-    return mul(mul(mul(rho_a * c_pa, c_aw), vel), sub(T_s, T_a));       // :165
+    const double rho_a = 1.225, c_pa = 1.008E+03;                                 // :151-152
+    const auto c_aw = M::sel_lt(T_a, T_s, M::bc(1.13E-03), M::bc(0.66E-03));      // :157-161
+    return M::mul(M::mul(M::mul(M::bc(rho_a * c_pa), c_aw), vel), M::sub(T_s, T_a));   // :165
 }
 
 // momentum/flux_momentum.F90:63-73; returns flux_air, the caller forms -flux_air*u / -flux_air*v
-FC_DI double momentum_flux_air_cclm(double a_momentum, double p_s, double q_s, double T_s, double vel,
-                                    const Consts &c)
+template <class M>
+FC_DI typename M::T momentum_flux_air_cclm(M &m, const typename M::T &a_momentum, const typename M::T &p_s,
+                                           const typename M::T &q_s, const typename M::T &T_s,
+                                           const typename M::T &vel, const Consts &c)
 {
-    const double T_tilde = t_tilde(T_s, q_s, c);                        // :63-65
-    return dvd(mul(mul(a_momentum, vel), p_s), mul(c.gas_constant_air, T_tilde));   // :69-70
+    const auto T_tilde = t_tilde<M>(T_s, q_s, c);                                 // :63-65
+    return m.div(M::mul(M::mul(a_momentum, vel), p_s), M::mul(M::bc(c.gas_constant_air), T_tilde));   // :69-70
 }
 
 // momentum/flux_momentum.F90:126-136; returns rho_a*c_aw*vel
-FC_DI double momentum_flux_air_rco(double vel)
+template <class M>
+FC_DI typename M::T momentum_flux_air_rco(const typename M::T &vel)
 {
-    const double rho_a = 1.225;                                         // :122
-    const double c_aw = (vel < 11.0) ? 1.2E-03 : add(0.49E-03, mul(0.065E-03, vel));   // :129-133
-    return mul(mul(rho_a, c_aw), vel);
+    const double rho_a = 1.225;                                                   // :122
+    const auto c_aw = M::sel_lt(vel, M::bc(11.0), M::bc(1.2E-03),
+                                M::add(M::bc(0.49E-03), M::mul(M::bc(0.065E-03), vel)));   // :129-133
+    return M::mul(M::mul(M::bc(rho_a), c_aw), vel);
 }
 
-FC_DI double momentum_component(double flux_air, double wind) { return -mul(flux_air, wind); }   // :72-73 / :135-136
+template <class M>
+FC_DI typename M::T momentum_component(const typename M::T &flux_air, const typename M::T &wind)
+{
+    return M::neg(M::mul(flux_air, wind));                                        // :72-73 / :135-136
+}
 
 // radiation/flux_radiation_blackbody.F90:40: sigma * T**4, integer power == (T*T)*(T*T)
-FC_DI double flux_radiation_blackbody_StBo(double T_s, double sigma)
+template <class M>
+FC_DI typename M::T flux_radiation_blackbody_StBo(const typename M::T &T_s, double sigma)
 {
-    const double T2 = mul(T_s, T_s);
-    return mul(sigma, mul(T2, T2));
+    const auto T2 = M::mul(T_s, T_s);
+    return M::mul(M::bc(sigma), M::mul(T2, T2));
 }
 
 }  // namespace fc

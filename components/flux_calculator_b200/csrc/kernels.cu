@@ -20,40 +20,44 @@ namespace fc {
 // ---------------------------------------------------------------------------------------------
 // vector helpers
 // ---------------------------------------------------------------------------------------------
-struct V2 {
-    double v[kFusedVec];
-};
+constexpr int V = kFusedVec;
+using V2 = Vd<V>;
+using Fast = FastVec<V>;
+using Exact = ExactVec<V>;
 
-template <bool AL>
+// FULL: all V cells of this thread are inside the grid and every array is 16-byte aligned -> one 128-bit
+// access; otherwise (last thread of a ragged grid, misaligned user pointers) guarded scalar accesses
+template <bool FULL>
 __device__ __forceinline__ V2 ldv(const double *__restrict__ p, int64_t j, int nv)
 {
     V2 r;
-    if (AL && nv == kFusedVec) {
+    if (FULL) {
+        static_assert(V == 2, "128-bit path assumes 2 cells per thread");
         const double2 t = __ldg(reinterpret_cast<const double2 *>(p + j));
         r.v[0] = t.x;
         r.v[1] = t.y;
     } else {
 #pragma unroll
-        for (int k = 0; k < kFusedVec; ++k) r.v[k] = (k < nv) ? __ldg(p + j + k) : 1.0;
+        for (int k = 0; k < V; ++k) r.v[k] = (k < nv) ? __ldg(p + j + k) : 1.0;
     }
     return r;
 }
 
-template <bool AL>
+template <bool FULL>
 __device__ __forceinline__ void stv(double *p, int64_t j, int nv, const V2 &x)
 {
-    if (AL && nv == kFusedVec) {
+    if (FULL) {
         *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
     } else {
 #pragma unroll
-        for (int k = 0; k < kFusedVec; ++k)
+        for (int k = 0; k < V; ++k)
             if (k < nv) p[j + k] = x.v[k];
     }
 }
 
 // a field loaded at most once per distinct pointer: atmosphere fields are aliased into every
 // surface type (distribute_input_field, basic.F90:334-358), so consecutive types usually share them
-template <bool AL>
+template <bool FULL>
 struct Cached {
     const double *ptr = nullptr;
     V2 val;
@@ -61,188 +65,190 @@ struct Cached {
     {
         if (p != ptr) {
             ptr = p;
-            if (p) val = ldv<AL>(p, j, nv);
+            if (p) val = ldv<FULL>(p, j, nv);
         }
         return val;
     }
 };
 
+__device__ __forceinline__ V2 vzero()
+{
+    V2 r;
+#pragma unroll
+    for (int k = 0; k < V; ++k) r.v[k] = 0.0;
+    return r;
+}
+
+// acc = acc + x*fare, separate multiply and add (average_across_surface_types, calculate.F90:379-382)
+__device__ __forceinline__ void avg_acc(V2 &acc, const V2 &x, const V2 &fare)
+{
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc.v[k] = add(acc.v[k], mul(x.v[k], fare.v[k]));
+}
+
 // ---------------------------------------------------------------------------------------------
-// diagnostics accumulation: (sum area*x, min, max) per slot
+// diagnostics: DIAG == 1: sum_j area_j*x_j ; DIAG == 2: additionally min_j x_j and max_j x_j.
+// thread partial -> warp shuffle tree -> lane 0 stores the warp's partial to global memory:
+// partials[plane][compact slot][warp row], planes = (sum, min, max).  No shared memory, no CTA barrier;
+// two tiny deterministic kernels combine the rows afterwards (diag_reduce_rows / diag_reduce_final).
 // ---------------------------------------------------------------------------------------------
-struct DiagAcc {
-    double s, mn, mx;
+struct DiagCtx {
+    double *base;        // partials
+    int64_t rows;        // row stride (total warp rows of the launch)
+    int64_t row;         // this warp's row
+    int64_t plane;       // slots * rows
 };
 
-__device__ __forceinline__ DiagAcc diag_cells(const V2 &x, const V2 &area, int nv)
+template <int DIAG>
+__device__ __forceinline__ void diag_commit(const FusedPlan &p, const DiagCtx &d, int slot, const V2 &x, const V2 &area, int nv)
 {
-    DiagAcc a{0.0, DBL_MAX, -DBL_MAX};
+    double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
 #pragma unroll
-    for (int k = 0; k < kFusedVec; ++k)
+    for (int k = 0; k < V; ++k)
         if (k < nv) {
-            a.s = add(a.s, mul(area.v[k], x.v[k]));
-            a.mn = fmin(a.mn, x.v[k]);
-            a.mx = fmax(a.mx, x.v[k]);
+            s = add(s, mul(area.v[k], x.v[k]));
+            if (DIAG >= 2) {
+                mn = fmin(mn, x.v[k]);
+                mx = fmax(mx, x.v[k]);
+            }
         }
-    return a;
-}
-
-__device__ __forceinline__ void diag_warp_commit(DiagAcc a, double *smem_slot /* [warps][3] base of this slot */)
-{
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-        a.s = add(a.s, __shfl_down_sync(0xffffffffu, a.s, off));
-        a.mn = fmin(a.mn, __shfl_down_sync(0xffffffffu, a.mn, off));
-        a.mx = fmax(a.mx, __shfl_down_sync(0xffffffffu, a.mx, off));
+        s = add(s, __shfl_down_sync(0xffffffffu, s, off));
+        if (DIAG >= 2) {
+            mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
+            mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+        }
     }
     if ((threadIdx.x & 31) == 0) {
-        double *d = smem_slot + (threadIdx.x >> 5) * 3;
-        d[0] = a.s;
-        d[1] = a.mn;
-        d[2] = a.mx;
+        double *o = d.base + (int64_t)p.diag_map[slot] * d.rows + d.row;
+        o[0] = s;
+        if (DIAG >= 2) {
+            o[d.plane] = mn;
+            o[2 * d.plane] = mx;
+        }
     }
 }
-
-constexpr int kWarps = kFusedThreads / 32;
-// shared layout: [compact slot][warp][3]; p.diag_map[slot] = compact index of an active slot
-#define DIAG_SMEM(slot) (diag_smem + (size_t)(p.diag_map[(slot)]) * kWarps * 3)
+#define DIAG_COMMIT(slot, x) diag_commit<DIAG>(p, dg, (slot), (x), area, nv)
 
 // ---------------------------------------------------------------------------------------------
-// fused chains
+// per-surface-type arithmetic of the t grid, instantiated with the fast and the exact policy
 // ---------------------------------------------------------------------------------------------
-template <int SS, bool DIAG, bool AL>
-__device__ __forceinline__ void t_chain(const FusedPlan &p, int blk, double *diag_smem)
+struct TIn {
+    V2 fice, psur, tsur, qatm, tatm, patm, uatm, vatm, aev, ase, qsur_in, bias;
+};
+struct TOut {
+    V2 qsur, meva, hlat, hsen, rbbr;
+};
+
+template <class M>
+__device__ __forceinline__ bool t_type_math(const FusedPlan &p, const FusedTType &ty, const TIn &in, bool has_bias, TOut &o)
+{
+    M m;
+    const Consts &c = p.c;
+    if (p.do_normal) {
+        // --- QSUR: calc_spec_vapor_surface (calculate.F90:25-50)
+        if (ty.m_qsur == M_CCLM) o.qsur = spec_vapor_surface_cclm(m, in.fice, in.psur, in.tsur, c);
+        else o.qsur = in.qsur_in;
+        V2 vel;
+        if (ty.m_meva >= M_CCLM || ty.m_hsen >= M_CCLM) vel = wind_speed(m, in.uatm, in.vatm);
+        // --- MEVA: calc_flux_mass_evap (calculate.F90:54-120); T slot <- TATM (:87,:98)
+        if (ty.m_meva != M_NONE) {
+            if (ty.m_meva == M_CCLM || ty.m_meva == M_MOM5)
+                o.meva = flux_mass_evap_cclm(m, in.aev, in.psur, in.qatm, o.qsur, in.tatm, vel, c);
+            else if (ty.m_meva == M_RCO)
+                o.meva = flux_mass_evap_rco(m, in.qatm, in.tsur, vel);
+            else
+                o.meva = vzero();                                              // 'zero' (:79)
+            if (has_bias) o.meva = M::add(o.meva, in.bias);                    // :112-116
+        }
+        // --- HLAT: calc_flux_heat_latent (calculate.F90:124-154), sees the corrected MEVA
+        if (ty.m_hlat != M_NONE)
+            o.hlat = (ty.m_hlat == M_ZERO) ? vzero() : M::mul(o.meva, M::bc(ty.latent_heat));   // heat_latent.F90:41,65
+        // --- HSEN: calc_flux_heat_sensible (calculate.F90:156-208); q_s slot <- QATM (:178,:190)
+        if (ty.m_hsen != M_NONE) {
+            if (ty.m_hsen == M_CCLM || ty.m_hsen == M_MOM5)
+                o.hsen = flux_heat_sensible_cclm(m, in.ase, in.patm, in.psur, in.qatm, in.tatm, in.tsur, vel, c);
+            else if (ty.m_hsen == M_RCO)
+                o.hsen = flux_heat_sensible_rco<M>(in.tatm, in.tsur, vel);
+            else
+                o.hsen = vzero();
+        }
+    }
+    // --- RBBR: calc_flux_radiation_blackbody (calculate.F90:320-345), early phase
+    if (p.do_early && ty.m_rbbr != M_NONE)
+        o.rbbr = (ty.m_rbbr == M_ZERO) ? vzero() : flux_radiation_blackbody_StBo<M>(in.tsur, c.stefan_boltzmann_constant);
+    return m.bad();
+}
+
+// recompute path (an operand left the range in which the lock-step sequences are proven): out of line, cold
+__device__ __noinline__ void t_type_exact(const FusedPlan &p, const FusedTType &ty, const TIn &in, bool has_bias, TOut &o)
+{
+    t_type_math<Exact>(p, ty, in, has_bias, o);
+}
+
+template <int SS, int DIAG, bool FULL>
+__device__ __forceinline__ void t_chain(const FusedPlan &p, int64_t j, int nv, const DiagCtx &dg)
 {
     const FusedT &t = p.t;
-    const Consts &c = p.c;
-    const int64_t end = p.cell0[0] + p.cells[0];
-    const int64_t j = p.cell0[0] + ((int64_t)blk * kFusedThreads + threadIdx.x) * kFusedVec;
-    const int nv = (j >= end) ? 0 : (end - j >= kFusedVec ? kFusedVec : (int)(end - j));
-    if (!DIAG && nv == 0) return;
     const int S = SS ? SS : p.S;
-
-    Cached<AL> cPSUR, cQATM, cTATM, cPATM, cUATM, cVATM, cAEV, cASE, cFICE, cTSUR;
-    V2 bias, rsdd, area;
+    Cached<FULL> cPSUR, cQATM, cTATM, cPATM, cUATM, cVATM, cAEV, cASE, cFICE, cTSUR;
+    TIn in;
+    V2 rsdd, area;
     const bool has_bias = p.do_normal && t.bias != nullptr;
     const bool has_rsdr = p.do_normal && t.rsdd != nullptr;
-    if (nv) {
-        if (has_bias) bias = ldv<AL>(t.bias, j, nv);
-        if (has_rsdr) rsdd = ldv<AL>(t.rsdd, j, nv);
-        if (DIAG) area = ldv<AL>(t.area, j, nv);
-    }
-
-    V2 aQ, aM, aL, aH, aR;   // type-0 averages, sequential from 0.0 (calculate.F90:377-383)
-#pragma unroll
-    for (int k = 0; k < kFusedVec; ++k) aQ.v[k] = aM.v[k] = aL.v[k] = aH.v[k] = aR.v[k] = 0.0;
-    V2 aS = aQ;
+    if (has_bias) in.bias = ldv<FULL>(t.bias, j, nv);
+    if (has_rsdr) rsdd = ldv<FULL>(t.rsdd, j, nv);
+    if (DIAG) area = ldv<FULL>(t.area, j, nv);
+    V2 aQ = vzero(), aM = vzero(), aL = vzero(), aH = vzero(), aR = vzero(), aS = vzero();   // type-0 averages
 
     auto per_type = [&](const int i) {
         const FusedTType &ty = t.ty[i];
-        V2 qsur, meva, hlat, hsen, rbbr, fare;
-        if (nv) {
-            const V2 &tsur = cTSUR.get(ty.tsur, j, nv);
-            if (ty.fare) fare = ldv<AL>(ty.fare, j, nv);
+        V2 fare;
+        TOut o;
+        if (FULL || nv) {
+            // all loads of this surface type up front (memory-level parallelism), then arithmetic
+            in.tsur = cTSUR.get(ty.tsur, j, nv);
+            if (ty.fare) fare = ldv<FULL>(ty.fare, j, nv);
             if (p.do_normal) {
-                const V2 &psur = cPSUR.get(ty.psur, j, nv);
-                const V2 &qatm = cQATM.get(ty.qatm, j, nv);
-                const V2 &tatm = cTATM.get(ty.tatm, j, nv);
-                const V2 &uatm = cUATM.get(ty.uatm, j, nv);
-                const V2 &vatm = cVATM.get(ty.vatm, j, nv);
-                // --- QSUR: calc_spec_vapor_surface (calculate.F90:25-50)
-                if (ty.m_qsur == M_CCLM) {
-                    const V2 &fice = cFICE.get(ty.fice, j, nv);
-#pragma unroll
-                    for (int k = 0; k < kFusedVec; ++k)
-                        qsur.v[k] = spec_vapor_surface_cclm(fice.v[k], psur.v[k], tsur.v[k], c);
-                    stv<AL>(ty.qsur, j, nv, qsur);
-                } else if (ty.qsur_in) {
-                    qsur = ldv<AL>(ty.qsur_in, j, nv);
-                }
-                V2 vel;
-#pragma unroll
-                for (int k = 0; k < kFusedVec; ++k) vel.v[k] = wind_speed(uatm.v[k], vatm.v[k]);
-                // --- MEVA: calc_flux_mass_evap (calculate.F90:54-120); T slot <- TATM (:87,:98)
-                if (ty.m_meva != M_NONE) {
-                    if (ty.m_meva == M_CCLM || ty.m_meva == M_MOM5) {
-                        const V2 &a = cAEV.get(ty.a_evap, j, nv);
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k)
-                            meva.v[k] = flux_mass_evap_cclm(a.v[k], psur.v[k], qatm.v[k], qsur.v[k], tatm.v[k],
-                                                            vel.v[k], c);
-                    } else if (ty.m_meva == M_RCO) {
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k)
-                            meva.v[k] = flux_mass_evap_rco(qatm.v[k], tsur.v[k], vel.v[k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k) meva.v[k] = 0.0;   // 'zero' (:79)
-                    }
-                    if (has_bias) {                                            // :112-116
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k) meva.v[k] = add(meva.v[k], bias.v[k]);
-                    }
-                    stv<AL>(ty.meva, j, nv, meva);
-                }
-                // --- HLAT: calc_flux_heat_latent (calculate.F90:124-154), sees the corrected MEVA
-                if (ty.m_hlat != M_NONE) {
-#pragma unroll
-                    for (int k = 0; k < kFusedVec; ++k)
-                        hlat.v[k] = (ty.m_hlat == M_ZERO) ? 0.0 : flux_heat_latent(meva.v[k], ty.latent_heat);
-                    stv<AL>(ty.hlat, j, nv, hlat);
-                }
-                // --- HSEN: calc_flux_heat_sensible (calculate.F90:156-208); q_s slot <- QATM (:178,:190)
-                if (ty.m_hsen != M_NONE) {
-                    if (ty.m_hsen == M_CCLM || ty.m_hsen == M_MOM5) {
-                        const V2 &a = cASE.get(ty.a_sens, j, nv);
-                        const V2 &patm = cPATM.get(ty.patm, j, nv);
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k)
-                            hsen.v[k] = flux_heat_sensible_cclm(a.v[k], patm.v[k], psur.v[k], qatm.v[k], tatm.v[k],
-                                                                tsur.v[k], vel.v[k], c);
-                    } else if (ty.m_hsen == M_RCO) {
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k)
-                            hsen.v[k] = flux_heat_sensible_rco(tatm.v[k], tsur.v[k], vel.v[k]);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k) hsen.v[k] = 0.0;
-                    }
-                    stv<AL>(ty.hsen, j, nv, hsen);
-                }
-                // --- RSDR: distribute_shortwave_radiation_flux (calculate.F90:347-364)
-                if (has_rsdr) stv<AL>(ty.rsdr, j, nv, rsdd);
+                in.psur = cPSUR.get(ty.psur, j, nv);
+                in.qatm = cQATM.get(ty.qatm, j, nv);
+                in.tatm = cTATM.get(ty.tatm, j, nv);
+                in.uatm = cUATM.get(ty.uatm, j, nv);
+                in.vatm = cVATM.get(ty.vatm, j, nv);
+                in.fice = cFICE.get(ty.fice, j, nv);
+                in.aev = cAEV.get(ty.a_evap, j, nv);
+                in.ase = cASE.get(ty.a_sens, j, nv);
+                in.patm = cPATM.get(ty.patm, j, nv);
+                if (ty.qsur_in) in.qsur_in = ldv<FULL>(ty.qsur_in, j, nv);
             }
-            // --- RBBR: calc_flux_radiation_blackbody (calculate.F90:320-345), early phase
-            if (p.do_early && ty.m_rbbr != M_NONE) {
-#pragma unroll
-                for (int k = 0; k < kFusedVec; ++k)
-                    rbbr.v[k] = (ty.m_rbbr == M_ZERO)
-                                    ? 0.0
-                                    : flux_radiation_blackbody_StBo(tsur.v[k], c.stefan_boltzmann_constant);
-                stv<AL>(ty.rbbr, j, nv, rbbr);
+            if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
+                t_type_exact(p, ty, in, has_bias, o);             // redo these cells with the IEEE routines
+            if (p.do_normal) {
+                if (ty.m_qsur == M_CCLM) stv<FULL>(ty.qsur, j, nv, o.qsur);
+                if (ty.m_meva != M_NONE) stv<FULL>(ty.meva, j, nv, o.meva);
+                if (ty.m_hlat != M_NONE) stv<FULL>(ty.hlat, j, nv, o.hlat);
+                if (ty.m_hsen != M_NONE) stv<FULL>(ty.hsen, j, nv, o.hsen);
+                if (has_rsdr) stv<FULL>(ty.rsdr, j, nv, rsdd);                 // calculate.F90:347-364
             }
-            // --- average_across_surface_types (calculate.F90:368-385): acc = acc + X(i)*FARE(i)
-#pragma unroll
-            for (int k = 0; k < kFusedVec; ++k) {
-                if (t.avg_qsur) aQ.v[k] = add(aQ.v[k], mul(qsur.v[k], fare.v[k]));
-                if (t.avg_meva) aM.v[k] = add(aM.v[k], mul(meva.v[k], fare.v[k]));
-                if (t.avg_hlat) aL.v[k] = add(aL.v[k], mul(hlat.v[k], fare.v[k]));
-                if (t.avg_hsen) aH.v[k] = add(aH.v[k], mul(hsen.v[k], fare.v[k]));
-                if (t.avg_rbbr) aR.v[k] = add(aR.v[k], mul(rbbr.v[k], fare.v[k]));
-                if (t.avg_rsdr) aS.v[k] = add(aS.v[k], mul(rsdd.v[k], fare.v[k]));
-            }
+            if (p.do_early && ty.m_rbbr != M_NONE) stv<FULL>(ty.rbbr, j, nv, o.rbbr);
+            if (t.avg_qsur) avg_acc(aQ, o.qsur, fare);
+            if (t.avg_meva) avg_acc(aM, o.meva, fare);
+            if (t.avg_hlat) avg_acc(aL, o.hlat, fare);
+            if (t.avg_hsen) avg_acc(aH, o.hsen, fare);
+            if (t.avg_rbbr) avg_acc(aR, o.rbbr, fare);
+            if (t.avg_rsdr) avg_acc(aS, rsdd, fare);
         }
         if (DIAG) {
             const int base = (i + 1) * DQ_COUNT;
             if (p.do_normal) {
-                if (ty.m_qsur == M_CCLM) diag_warp_commit(diag_cells(qsur, area, nv), DIAG_SMEM(base + DQ_QSUR_T));
-                if (ty.m_meva != M_NONE) diag_warp_commit(diag_cells(meva, area, nv), DIAG_SMEM(base + DQ_MEVA));
-                if (ty.m_hlat != M_NONE) diag_warp_commit(diag_cells(hlat, area, nv), DIAG_SMEM(base + DQ_HLAT));
-                if (ty.m_hsen != M_NONE) diag_warp_commit(diag_cells(hsen, area, nv), DIAG_SMEM(base + DQ_HSEN));
-                if (has_rsdr) diag_warp_commit(diag_cells(rsdd, area, nv), DIAG_SMEM(base + DQ_RSDR));
+                if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base + DQ_QSUR_T, o.qsur);
+                if (ty.m_meva != M_NONE) DIAG_COMMIT(base + DQ_MEVA, o.meva);
+                if (ty.m_hlat != M_NONE) DIAG_COMMIT(base + DQ_HLAT, o.hlat);
+                if (ty.m_hsen != M_NONE) DIAG_COMMIT(base + DQ_HSEN, o.hsen);
+                if (has_rsdr) DIAG_COMMIT(base + DQ_RSDR, rsdd);
             }
-            if (p.do_early && ty.m_rbbr != M_NONE)
-                diag_warp_commit(diag_cells(rbbr, area, nv), DIAG_SMEM(base + DQ_RBBR));
+            if (p.do_early && ty.m_rbbr != M_NONE) DIAG_COMMIT(base + DQ_RBBR, o.rbbr);
         }
     };
     if constexpr (SS > 0) {
@@ -252,98 +258,96 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, int blk, double *dia
 #pragma unroll 1
         for (int i = 0; i < S; ++i) per_type(i);
     }
-    if (nv) {
-        if (t.avg_qsur) stv<AL>(t.avg_qsur, j, nv, aQ);
-        if (t.avg_meva) stv<AL>(t.avg_meva, j, nv, aM);
-        if (t.avg_hlat) stv<AL>(t.avg_hlat, j, nv, aL);
-        if (t.avg_hsen) stv<AL>(t.avg_hsen, j, nv, aH);
-        if (t.avg_rbbr) stv<AL>(t.avg_rbbr, j, nv, aR);
-        if (t.avg_rsdr) stv<AL>(t.avg_rsdr, j, nv, aS);
+    if (FULL || nv) {
+        if (t.avg_qsur) stv<FULL>(t.avg_qsur, j, nv, aQ);
+        if (t.avg_meva) stv<FULL>(t.avg_meva, j, nv, aM);
+        if (t.avg_hlat) stv<FULL>(t.avg_hlat, j, nv, aL);
+        if (t.avg_hsen) stv<FULL>(t.avg_hsen, j, nv, aH);
+        if (t.avg_rbbr) stv<FULL>(t.avg_rbbr, j, nv, aR);
+        if (t.avg_rsdr) stv<FULL>(t.avg_rsdr, j, nv, aS);
     }
     if (DIAG) {
-        if (t.avg_qsur) diag_warp_commit(diag_cells(aQ, area, nv), DIAG_SMEM(DQ_QSUR_T));
-        if (t.avg_meva) diag_warp_commit(diag_cells(aM, area, nv), DIAG_SMEM(DQ_MEVA));
-        if (t.avg_hlat) diag_warp_commit(diag_cells(aL, area, nv), DIAG_SMEM(DQ_HLAT));
-        if (t.avg_hsen) diag_warp_commit(diag_cells(aH, area, nv), DIAG_SMEM(DQ_HSEN));
-        if (t.avg_rbbr) diag_warp_commit(diag_cells(aR, area, nv), DIAG_SMEM(DQ_RBBR));
-        if (t.avg_rsdr) diag_warp_commit(diag_cells(aS, area, nv), DIAG_SMEM(DQ_RSDR));
+        if (t.avg_qsur) DIAG_COMMIT(DQ_QSUR_T, aQ);
+        if (t.avg_meva) DIAG_COMMIT(DQ_MEVA, aM);
+        if (t.avg_hlat) DIAG_COMMIT(DQ_HLAT, aL);
+        if (t.avg_hsen) DIAG_COMMIT(DQ_HSEN, aH);
+        if (t.avg_rbbr) DIAG_COMMIT(DQ_RBBR, aR);
+        if (t.avg_rsdr) DIAG_COMMIT(DQ_RSDR, aS);
     }
 }
 
-template <int SS, bool DIAG, bool AL>
-__device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, int which, int blk, double *diag_smem)
+// ---------------------------------------------------------------------------------------------
+// u / v grid
+// ---------------------------------------------------------------------------------------------
+struct UVIn {
+    V2 fice, psur, tsur, amom, uatm, vatm, qsur_in;
+};
+struct UVOut {
+    V2 qsur, mom;
+};
+
+template <class M>
+__device__ __forceinline__ bool uv_type_math(const FusedPlan &p, const FusedUVType &ty, const UVIn &in, int north, UVOut &o)
 {
+    M m;
     const Consts &c = p.c;
-    const int64_t end = p.cell0[which] + p.cells[which];
-    const int64_t j = p.cell0[which] + ((int64_t)blk * kFusedThreads + threadIdx.x) * kFusedVec;
-    const int nv = (j >= end) ? 0 : (end - j >= kFusedVec ? kFusedVec : (int)(end - j));
-    if (!DIAG && nv == 0) return;
+    // --- QSUR on this grid (calculate.F90:25-50, called for grids 2 and 3)
+    if (ty.m_qsur == M_CCLM) o.qsur = spec_vapor_surface_cclm(m, in.fice, in.psur, in.tsur, c);
+    else o.qsur = in.qsur_in;
+    // --- momentum: calc_flux_momentum_east / _north (calculate.F90:212-316)
+    if (ty.m_mom != M_NONE) {
+        if (ty.m_mom == M_ZERO) {
+            o.mom = vzero();
+        } else {
+            const V2 vel = wind_speed(m, in.uatm, in.vatm);
+            const V2 fa = (ty.m_mom == M_RCO) ? momentum_flux_air_rco<M>(vel)
+                                              : momentum_flux_air_cclm(m, in.amom, in.psur, o.qsur, in.tsur, vel, c);
+            o.mom = momentum_component<M>(fa, north ? in.vatm : in.uatm);
+        }
+    }
+    return m.bad();
+}
+
+__device__ __noinline__ void uv_type_exact(const FusedPlan &p, const FusedUVType &ty, const UVIn &in, int north, UVOut &o)
+{
+    uv_type_math<Exact>(p, ty, in, north, o);
+}
+
+template <int SS, int DIAG, bool FULL>
+__device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, int which, int64_t j, int nv, const DiagCtx &dg)
+{
     const int S = SS ? SS : p.S;
     const int dq_q = (which == 1) ? DQ_QSUR_U : DQ_QSUR_V;
     const int dq_m = (which == 1) ? DQ_UMOM : DQ_VMOM;
-
-    Cached<AL> cPSUR, cUATM, cVATM, cAMOM, cFICE, cTSUR;
+    Cached<FULL> cPSUR, cUATM, cVATM, cAMOM, cFICE, cTSUR;
+    UVIn in;
     V2 area;
-    if (DIAG && nv) area = ldv<AL>(g.area, j, nv);
-    V2 aQ, aM;
-#pragma unroll
-    for (int k = 0; k < kFusedVec; ++k) aQ.v[k] = aM.v[k] = 0.0;
+    if (DIAG) area = ldv<FULL>(g.area, j, nv);
+    V2 aQ = vzero(), aM = vzero();
 
     auto per_type = [&](const int i) {
         const FusedUVType &ty = g.ty[i];
-        V2 qsur, mom, fare;
-        if (nv) {
-            if (ty.fare) fare = ldv<AL>(ty.fare, j, nv);
-            // --- QSUR on this grid (calculate.F90:25-50, called for grids 2 and 3)
-            if (ty.m_qsur == M_CCLM) {
-                const V2 &fice = cFICE.get(ty.fice, j, nv);
-                const V2 &psur = cPSUR.get(ty.psur, j, nv);
-                const V2 &tsur = cTSUR.get(ty.tsur, j, nv);
-#pragma unroll
-                for (int k = 0; k < kFusedVec; ++k)
-                    qsur.v[k] = spec_vapor_surface_cclm(fice.v[k], psur.v[k], tsur.v[k], c);
-                stv<AL>(ty.qsur, j, nv, qsur);
-            } else if (ty.qsur_in) {
-                qsur = ldv<AL>(ty.qsur_in, j, nv);
-            }
-            // --- momentum: calc_flux_momentum_east / _north (calculate.F90:212-316)
-            if (ty.m_mom != M_NONE) {
-                if (ty.m_mom == M_ZERO) {
-#pragma unroll
-                    for (int k = 0; k < kFusedVec; ++k) mom.v[k] = 0.0;
-                } else {
-                    const V2 &uatm = cUATM.get(ty.uatm, j, nv);
-                    const V2 &vatm = cVATM.get(ty.vatm, j, nv);
-                    if (ty.m_mom == M_RCO) {
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k) {
-                            const double vel = wind_speed(uatm.v[k], vatm.v[k]);
-                            mom.v[k] = momentum_component(momentum_flux_air_rco(vel), g.north ? vatm.v[k] : uatm.v[k]);
-                        }
-                    } else {
-                        const V2 &a = cAMOM.get(ty.a_mom, j, nv);
-                        const V2 &psur = cPSUR.get(ty.psur, j, nv);
-                        const V2 &tsur = cTSUR.get(ty.tsur, j, nv);
-#pragma unroll
-                        for (int k = 0; k < kFusedVec; ++k) {
-                            const double vel = wind_speed(uatm.v[k], vatm.v[k]);
-                            const double fa = momentum_flux_air_cclm(a.v[k], psur.v[k], qsur.v[k], tsur.v[k], vel, c);
-                            mom.v[k] = momentum_component(fa, g.north ? vatm.v[k] : uatm.v[k]);
-                        }
-                    }
-                }
-                stv<AL>(ty.mom, j, nv, mom);
-            }
-#pragma unroll
-            for (int k = 0; k < kFusedVec; ++k) {
-                if (g.avg_qsur) aQ.v[k] = add(aQ.v[k], mul(qsur.v[k], fare.v[k]));
-                if (g.avg_mom) aM.v[k] = add(aM.v[k], mul(mom.v[k], fare.v[k]));
-            }
+        V2 fare;
+        UVOut o;
+        if (FULL || nv) {
+            if (ty.fare) fare = ldv<FULL>(ty.fare, j, nv);
+            in.fice = cFICE.get(ty.fice, j, nv);
+            in.psur = cPSUR.get(ty.psur, j, nv);
+            in.tsur = cTSUR.get(ty.tsur, j, nv);
+            in.uatm = cUATM.get(ty.uatm, j, nv);
+            in.vatm = cVATM.get(ty.vatm, j, nv);
+            in.amom = cAMOM.get(ty.a_mom, j, nv);
+            if (ty.qsur_in) in.qsur_in = ldv<FULL>(ty.qsur_in, j, nv);
+            if (uv_type_math<Fast>(p, ty, in, g.north, o)) uv_type_exact(p, ty, in, g.north, o);
+            if (ty.m_qsur == M_CCLM) stv<FULL>(ty.qsur, j, nv, o.qsur);
+            if (ty.m_mom != M_NONE) stv<FULL>(ty.mom, j, nv, o.mom);
+            if (g.avg_qsur) avg_acc(aQ, o.qsur, fare);
+            if (g.avg_mom) avg_acc(aM, o.mom, fare);
         }
         if (DIAG) {
             const int base = (i + 1) * DQ_COUNT;
-            if (ty.m_qsur == M_CCLM) diag_warp_commit(diag_cells(qsur, area, nv), DIAG_SMEM(base + dq_q));
-            if (ty.m_mom != M_NONE) diag_warp_commit(diag_cells(mom, area, nv), DIAG_SMEM(base + dq_m));
+            if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base + dq_q, o.qsur);
+            if (ty.m_mom != M_NONE) DIAG_COMMIT(base + dq_m, o.mom);
         }
     };
     if constexpr (SS > 0) {
@@ -353,87 +357,194 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
 #pragma unroll 1
         for (int i = 0; i < S; ++i) per_type(i);
     }
-    if (nv) {
-        if (g.avg_qsur) stv<AL>(g.avg_qsur, j, nv, aQ);
-        if (g.avg_mom) stv<AL>(g.avg_mom, j, nv, aM);
+    if (FULL || nv) {
+        if (g.avg_qsur) stv<FULL>(g.avg_qsur, j, nv, aQ);
+        if (g.avg_mom) stv<FULL>(g.avg_mom, j, nv, aM);
     }
     if (DIAG) {
-        if (g.avg_qsur) diag_warp_commit(diag_cells(aQ, area, nv), DIAG_SMEM(dq_q));
-        if (g.avg_mom) diag_warp_commit(diag_cells(aM, area, nv), DIAG_SMEM(dq_m));
+        if (g.avg_qsur) DIAG_COMMIT(dq_q, aQ);
+        if (g.avg_mom) DIAG_COMMIT(dq_m, aM);
     }
 }
 
-template <int SS, bool DIAG, bool AL>
-__global__ void __launch_bounds__(kFusedThreads)
-fused_step_kernel(const __grid_constant__ FusedPlan p, int nb_t, int nb_u)
+// L2 prefetch of the tile a later CTA will work on: one bulk prefetch per input array, issued by one thread.
+// It needs no register or scoreboard slot, so DRAM latency is paid ahead of time and the demand loads of
+// CTA b+distance hit L2 (ncu: long_scoreboard was the dominant stall at 14-16 resident warps/SM).
+__device__ __forceinline__ void prefetch_l2(const double *p, int64_t cell, int64_t end)
 {
-    extern __shared__ double diag_smem[];
-    const int b = blockIdx.x;
-    if (DIAG) {
-        // neutral elements for every slot this block does not touch
-        for (int k = threadIdx.x; k < p.diag_n * kWarps; k += kFusedThreads) {
-            diag_smem[k * 3 + 0] = 0.0;
-            diag_smem[k * 3 + 1] = DBL_MAX;
-            diag_smem[k * 3 + 2] = -DBL_MAX;
+    if (p == nullptr || cell >= end) return;
+    const int64_t n = (end - cell) < kFusedCellsPerBlock ? (end - cell) : kFusedCellsPerBlock;
+    const uint32_t bytes = (uint32_t)(n * 8) & ~15u;
+    if (bytes)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p + cell), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void prefetch_tile(const FusedPlan &p, int which, int64_t cell, int64_t end)
+{
+    if (which == 0) {
+        const FusedT &t = p.t;
+        if (p.do_normal) {
+            prefetch_l2(t.bias, cell, end);
+            prefetch_l2(t.rsdd, cell, end);
         }
-        __syncthreads();
-    }
-    if (b < nb_t) {
-        if (p.do_normal || p.do_early) t_chain<SS, DIAG, AL>(p, b, diag_smem);
-    } else if (b < nb_t + nb_u) {
-        uv_chain<SS, DIAG, AL>(p, p.uv[0], 1, b - nb_t, diag_smem);
-    } else {
-        uv_chain<SS, DIAG, AL>(p, p.uv[1], 2, b - nb_t - nb_u, diag_smem);
-    }
-    if (DIAG) {
-        __syncthreads();
-        // fixed-order combine over the block's warps, one thread per slot
-        for (int s = threadIdx.x; s < p.diag_n; s += kFusedThreads) {
-            const double *w = diag_smem + (size_t)s * kWarps * 3;
-            double sum = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+        prefetch_l2(t.area, cell, end);
+        const double *last[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int i = 0; i < p.S; ++i) {
+            const FusedTType &ty = t.ty[i];
+            const double *q[8] = {ty.psur, ty.qatm, ty.tatm, ty.patm, ty.uatm, ty.vatm, ty.a_evap, ty.a_sens};
 #pragma unroll
-            for (int k = 0; k < kWarps; ++k) {
-                sum = add(sum, w[k * 3 + 0]);
-                mn = fmin(mn, w[k * 3 + 1]);
-                mx = fmax(mx, w[k * 3 + 2]);
+            for (int k = 0; k < 8; ++k)
+                if (q[k] != last[k]) {      // atmosphere fields are shared by the surface types
+                    last[k] = q[k];
+                    if (p.do_normal) prefetch_l2(q[k], cell, end);
+                }
+            prefetch_l2(ty.tsur, cell, end);
+            prefetch_l2(ty.fare, cell, end);
+            if (p.do_normal) {
+                prefetch_l2(ty.fice, cell, end);
+                prefetch_l2(ty.qsur_in, cell, end);
             }
-            double *o = p.diag_partials + ((size_t)b * p.diag_n + s) * 3;
-            o[0] = sum;
-            o[1] = mn;
-            o[2] = mx;
+        }
+    } else {
+        const FusedUV &g = p.uv[which - 1];
+        prefetch_l2(g.area, cell, end);
+        const double *last[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int i = 0; i < p.S; ++i) {
+            const FusedUVType &ty = g.ty[i];
+            const double *q[4] = {ty.psur, ty.uatm, ty.vatm, ty.a_mom};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (q[k] != last[k]) {
+                    last[k] = q[k];
+                    prefetch_l2(q[k], cell, end);
+                }
+            prefetch_l2(ty.fice, cell, end);
+            prefetch_l2(ty.tsur, cell, end);
+            prefetch_l2(ty.fare, cell, end);
+            prefetch_l2(ty.qsur_in, cell, end);
         }
     }
 }
 
-// partials[blocks][slots][3] -> out[slots][3]; blocks are combined in index order (deterministic)
-__global__ void diag_finalize_kernel(const double *__restrict__ partials, int nblocks, int nslots,
-                                     double *__restrict__ out)
+// FULL = true : every thread owns V whole cells and every array is 16-byte aligned (128-bit accesses only);
+//               launched over floor(cells/V) cell vectors per grid.
+// FULL = false: guarded scalar accesses; launched over the ragged remainder (cells % V) of each grid, or over
+//               everything when a bound array is not 16-byte aligned.  first[] = first cell of this launch.
+struct LaunchGeom {
+    int nb_t, nb_u;          // blocks of the t / u grid (the rest is the v grid)
+    int64_t first[3];        // first cell handled by this launch on each grid
+    int64_t count[3];        // cells handled by this launch on each grid
+    int64_t row0;            // first diagnostics row of this launch
+    int prefetch_distance;   // in blocks, 0 = off
+};
+
+template <int SS, int DIAG, bool FULL>
+__global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks)
+fused_step_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ LaunchGeom geo)
+{
+    const int b = blockIdx.x;
+    const int which = (b < geo.nb_t) ? 0 : (b < geo.nb_t + geo.nb_u ? 1 : 2);
+    const int blk = (which == 0) ? b : (which == 1 ? b - geo.nb_t : b - geo.nb_t - geo.nb_u);
+    const int64_t end = geo.first[which] + geo.count[which];
+    const int64_t j = geo.first[which] + ((int64_t)blk * kFusedThreads + threadIdx.x) * V;
+    const int nv = (j >= end) ? 0 : (end - j >= V ? V : (int)(end - j));
+    if (FULL && geo.prefetch_distance > 0 && threadIdx.x == 0)
+        prefetch_tile(p, which, geo.first[which] + (int64_t)(blk + geo.prefetch_distance) * kFusedCellsPerBlock, end);
+    DiagCtx dg;
+    if (DIAG) {
+        dg.base = p.diag_partials;
+        dg.rows = p.diag_rows;
+        dg.plane = (int64_t)p.diag_n * p.diag_rows;
+        dg.row = geo.row0 + (int64_t)b * (kFusedThreads / 32) + (threadIdx.x >> 5);
+    }
+    if (!DIAG && nv == 0) return;      // with DIAG even empty threads take part in the warp reductions
+    if (which == 0) t_chain<SS, DIAG, FULL>(p, j, FULL ? V : nv, dg);
+    else uv_chain<SS, DIAG, FULL>(p, p.uv[which - 1], which, j, FULL ? V : nv, dg);
+}
+
+// diagnostics reduction, deterministic (fixed tree, independent of scheduling):
+//   stage 1: grid (chunks, slots): CTA sums kDiagChunk warp rows of one slot -> tmp[plane][slot][chunk]
+//   stage 2: grid (slots): sums the chunks -> out[slot][3] (sum, min, max)
+constexpr int kDiagChunk = 4096;
+
+struct DiagRanges {
+    int64_t row_begin[3], row_end[3];     // main-launch rows of the t / u / v blocks
+    int64_t tail_begin[3], tail_end[3];   // tail-launch rows
+    signed char grid_of_slot[kDiagSlots]; // compact slot -> 0/1/2
+};
+
+__device__ __forceinline__ void block_combine(double &s, double &mn, double &mx, int planes)
 {
     __shared__ double sh[3][256];
-    const int slot = blockIdx.x;
-    double sum = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-    // each thread takes a contiguous range of blocks so the combine order is fixed
-    const int per = (nblocks + blockDim.x - 1) / blockDim.x;
-    const int b0 = threadIdx.x * per;
-    const int b1 = min(nblocks, b0 + per);
-    for (int b = b0; b < b1; ++b) {
-        const double *q = partials + ((size_t)b * nslots + slot) * 3;
-        sum = add(sum, q[0]);
-        mn = fmin(mn, q[1]);
-        mx = fmax(mx, q[2]);
-    }
-    sh[0][threadIdx.x] = sum;
+    sh[0][threadIdx.x] = s;
     sh[1][threadIdx.x] = mn;
     sh[2][threadIdx.x] = mx;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        sum = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-        for (int k = 0; k < (int)blockDim.x; ++k) {
-            sum = add(sum, sh[0][k]);
-            mn = fmin(mn, sh[1][k]);
-            mx = fmax(mx, sh[2][k]);
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) {
+            sh[0][threadIdx.x] = add(sh[0][threadIdx.x], sh[0][threadIdx.x + w]);
+            if (planes > 1) {
+                sh[1][threadIdx.x] = fmin(sh[1][threadIdx.x], sh[1][threadIdx.x + w]);
+                sh[2][threadIdx.x] = fmax(sh[2][threadIdx.x], sh[2][threadIdx.x + w]);
+            }
         }
-        out[slot * 3 + 0] = sum;
+        __syncthreads();
+    }
+    s = sh[0][0];
+    mn = sh[1][0];
+    mx = sh[2][0];
+}
+
+__global__ void __launch_bounds__(256)
+diag_reduce_rows_kernel(const double *__restrict__ part, int64_t rows, int nslots, int planes,
+                        const __grid_constant__ DiagRanges R, double *__restrict__ tmp, int nchunks)
+{
+    const int slot = blockIdx.y, chunk = blockIdx.x;
+    const int g = R.grid_of_slot[slot];
+    const int64_t plane = (int64_t)nslots * rows;
+    const double *col = part + (int64_t)slot * rows;
+    double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+    constexpr int per = kDiagChunk / 256;
+    const int64_t r0 = (int64_t)chunk * kDiagChunk + threadIdx.x * per;
+#pragma unroll 4
+    for (int k = 0; k < per; ++k) {
+        const int64_t r = r0 + k;
+        const bool in = (r >= R.row_begin[g] && r < R.row_end[g]) || (r >= R.tail_begin[g] && r < R.tail_end[g]);
+        if (in) {
+            s = add(s, col[r]);
+            if (planes > 1) {
+                mn = fmin(mn, col[plane + r]);
+                mx = fmax(mx, col[2 * plane + r]);
+            }
+        }
+    }
+    block_combine(s, mn, mx, planes);
+    if (threadIdx.x == 0) {
+        double *o = tmp + ((int64_t)slot * nchunks + chunk) * 3;
+        o[0] = s;
+        o[1] = mn;
+        o[2] = mx;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+diag_reduce_final_kernel(const double *__restrict__ tmp, int nchunks, int planes, double *__restrict__ out)
+{
+    const int slot = blockIdx.x;
+    double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+    const int per = (nchunks + 255) / 256;
+    for (int k = 0; k < per; ++k) {
+        const int c = threadIdx.x * per + k;
+        if (c < nchunks) {
+            const double *q = tmp + ((int64_t)slot * nchunks + c) * 3;
+            s = add(s, q[0]);
+            mn = fmin(mn, q[1]);
+            mx = fmax(mx, q[2]);
+        }
+    }
+    block_combine(s, mn, mx, planes);
+    if (threadIdx.x == 0) {
+        out[slot * 3 + 0] = s;
         out[slot * 3 + 1] = mn;
         out[slot * 3 + 2] = mx;
     }
@@ -447,6 +558,8 @@ __global__ void diag_finalize_kernel(const double *__restrict__ partials, int nb
 __global__ void __launch_bounds__(256) oplist_kernel(const __grid_constant__ OpList L, const __grid_constant__ Consts c,
                                                      int64_t n)
 {
+    using M = ExactScalar;
+    M m;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
         for (int o = 0; o < L.n; ++o) {
             const Op &op = L.ops[o];
@@ -454,40 +567,40 @@ __global__ void __launch_bounds__(256) oplist_kernel(const __grid_constant__ OpL
                 case OP_ZERO: op.out[j] = 0.0; break;
                 case OP_COPY: op.out[j] = op.in[0][j]; break;
                 case OP_QSUR_CCLM:
-                    op.out[j] = spec_vapor_surface_cclm(op.in[0][j], op.in[1][j], op.in[2][j], c);
+                    op.out[j] = spec_vapor_surface_cclm(m, op.in[0][j], op.in[1][j], op.in[2][j], c);
                     break;
                 case OP_MEVA_CCLM:
-                    op.out[j] = flux_mass_evap_cclm(op.in[0][j], op.in[1][j], op.in[2][j], op.in[3][j], op.in[4][j],
-                                                    wind_speed(op.in[5][j], op.in[6][j]), c);
+                    op.out[j] = flux_mass_evap_cclm(m, op.in[0][j], op.in[1][j], op.in[2][j], op.in[3][j], op.in[4][j],
+                                                    wind_speed(m, op.in[5][j], op.in[6][j]), c);
                     break;
                 case OP_MEVA_RCO:
-                    op.out[j] = flux_mass_evap_rco(op.in[0][j], op.in[1][j], wind_speed(op.in[2][j], op.in[3][j]));
+                    op.out[j] = flux_mass_evap_rco(m, op.in[0][j], op.in[1][j], wind_speed(m, op.in[2][j], op.in[3][j]));
                     break;
                 case OP_ADD: op.out[j] = add(op.out[j], op.in[0][j]); break;
                 case OP_SCALE: op.out[j] = mul(op.in[0][j], op.cst); break;
                 case OP_HSEN_CCLM:
-                    op.out[j] = flux_heat_sensible_cclm(op.in[0][j], op.in[1][j], op.in[2][j], op.in[3][j], op.in[4][j],
-                                                        op.in[5][j], wind_speed(op.in[6][j], op.in[7][j]), c);
+                    op.out[j] = flux_heat_sensible_cclm(m, op.in[0][j], op.in[1][j], op.in[2][j], op.in[3][j], op.in[4][j],
+                                                        op.in[5][j], wind_speed(m, op.in[6][j], op.in[7][j]), c);
                     break;
                 case OP_HSEN_RCO:
-                    op.out[j] = flux_heat_sensible_rco(op.in[0][j], op.in[1][j], wind_speed(op.in[2][j], op.in[3][j]));
+                    op.out[j] = flux_heat_sensible_rco<M>(op.in[0][j], op.in[1][j], wind_speed(m, op.in[2][j], op.in[3][j]));
                     break;
                 case OP_MOM_CCLM: {
                     const double u = op.in[4][j], v = op.in[5][j];
-                    const double fa = momentum_flux_air_cclm(op.in[0][j], op.in[1][j], op.in[2][j], op.in[3][j],
-                                                             wind_speed(u, v), c);
-                    if (op.out) op.out[j] = momentum_component(fa, u);
-                    if (op.out2) op.out2[j] = momentum_component(fa, v);
+                    const double fa = momentum_flux_air_cclm(m, op.in[0][j], op.in[1][j], op.in[2][j], op.in[3][j],
+                                                             wind_speed(m, u, v), c);
+                    if (op.out) op.out[j] = momentum_component<M>(fa, u);
+                    if (op.out2) op.out2[j] = momentum_component<M>(fa, v);
                     break;
                 }
                 case OP_MOM_RCO: {
                     const double u = op.in[0][j], v = op.in[1][j];
-                    const double fa = momentum_flux_air_rco(wind_speed(u, v));
-                    if (op.out) op.out[j] = momentum_component(fa, u);
-                    if (op.out2) op.out2[j] = momentum_component(fa, v);
+                    const double fa = momentum_flux_air_rco<M>(wind_speed(m, u, v));
+                    if (op.out) op.out[j] = momentum_component<M>(fa, u);
+                    if (op.out2) op.out2[j] = momentum_component<M>(fa, v);
                     break;
                 }
-                case OP_RBBR: op.out[j] = flux_radiation_blackbody_StBo(op.in[0][j], op.cst); break;
+                case OP_RBBR: op.out[j] = flux_radiation_blackbody_StBo<M>(op.in[0][j], op.cst); break;
                 case OP_MULADD: op.out[j] = add(op.out[j], mul(op.in[0][j], op.in[1][j])); break;
                 default: break;
             }
@@ -527,16 +640,6 @@ __global__ void regrid_csr_kernel(const int64_t *__restrict__ row_ptr, const int
 // ---------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------
-static inline int blocks_for(int64_t cells) { return (int)((cells + kFusedCellsPerBlock - 1) / kFusedCellsPerBlock); }
-
-int fused_grid_blocks(const FusedPlan &p)
-{
-    const int nb_t = (p.do_early || p.do_normal) ? blocks_for(p.cells[0]) : 0;
-    const int nb_u = p.do_normal ? blocks_for(p.cells[1]) : 0;
-    const int nb_v = p.do_normal ? blocks_for(p.cells[2]) : 0;
-    return nb_t + nb_u + nb_v;
-}
-
 static bool plan_aligned(const FusedPlan &p)
 {
     auto ok = [](const void *q, int64_t cell0) { return q == nullptr || ((reinterpret_cast<uintptr_t>(q) + cell0 * 8) & 15) == 0; };
@@ -564,48 +667,118 @@ static bool plan_aligned(const FusedPlan &p)
     return a;
 }
 
-template <int SS, bool DIAG, bool AL>
-static cudaError_t launch_fused_t(const FusedPlan &p, int nb_t, int nb_u, int nb, cudaStream_t stream)
+// geometry of the (up to) two launches of one fused step: whole 512-cell blocks through the 128-bit kernel,
+// the ragged remainder (or everything, if an array is misaligned) through the guarded kernel
+struct FusedGeom {
+    LaunchGeom main, tail;
+    int nb_main, nb_tail;
+};
+
+static FusedGeom fused_geometry(const FusedPlan &p)
 {
-    const size_t smem = DIAG ? sizeof(double) * p.diag_n * kWarps * 3 : 0;   // <= 110*8*3*8 = 21 KB
-    fused_step_kernel<SS, DIAG, AL><<<nb, kFusedThreads, smem, stream>>>(p, nb_t, nb_u);
+    FusedGeom G;
+    memset(&G, 0, sizeof G);
+    const bool al = plan_aligned(p);
+    int nbm[3], nbt[3];
+    for (int g = 0; g < 3; ++g) {
+        const bool active = (g == 0) ? (p.do_early || p.do_normal) : (p.do_normal != 0);
+        const int64_t cells = active ? p.cells[g] : 0;
+        const int64_t whole = al ? (cells / kFusedCellsPerBlock) : 0;
+        nbm[g] = (int)whole;
+        G.main.first[g] = p.cell0[g];
+        G.main.count[g] = whole * kFusedCellsPerBlock;
+        G.tail.first[g] = p.cell0[g] + whole * kFusedCellsPerBlock;
+        G.tail.count[g] = cells - whole * kFusedCellsPerBlock;
+        nbt[g] = (int)((G.tail.count[g] + kFusedCellsPerBlock - 1) / kFusedCellsPerBlock);
+    }
+    G.main.nb_t = nbm[0];
+    G.main.nb_u = nbm[1];
+    G.nb_main = nbm[0] + nbm[1] + nbm[2];
+    G.tail.nb_t = nbt[0];
+    G.tail.nb_u = nbt[1];
+    G.nb_tail = nbt[0] + nbt[1] + nbt[2];
+    G.main.row0 = 0;
+    G.tail.row0 = (int64_t)G.nb_main * (kFusedThreads / 32);
+    G.main.prefetch_distance = p.prefetch_distance;
+    G.tail.prefetch_distance = 0;
+    return G;
+}
+
+int64_t fused_diag_rows(const FusedPlan &p)
+{
+    const FusedGeom G = fused_geometry(p);
+    return (int64_t)(G.nb_main + G.nb_tail) * (kFusedThreads / 32);
+}
+
+template <int SS, int DIAG>
+static cudaError_t launch_fused_t(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream, int *launches)
+{
+    if (G.nb_main) {
+        fused_step_kernel<SS, DIAG, true><<<G.nb_main, kFusedThreads, 0, stream>>>(p, G.main);
+        if (launches) *launches += 1;
+    }
+    if (G.nb_tail) {
+        fused_step_kernel<SS, DIAG, false><<<G.nb_tail, kFusedThreads, 0, stream>>>(p, G.tail);
+        if (launches) *launches += 1;
+    }
     return cudaGetLastError();
 }
 
 template <int SS>
-static cudaError_t launch_fused_s(const FusedPlan &p, int nb_t, int nb_u, int nb, bool al, cudaStream_t stream)
+static cudaError_t launch_fused_s(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream, int *launches)
 {
-    if (p.diag)
-        return al ? launch_fused_t<SS, true, true>(p, nb_t, nb_u, nb, stream)
-                  : launch_fused_t<SS, true, false>(p, nb_t, nb_u, nb, stream);
-    return al ? launch_fused_t<SS, false, true>(p, nb_t, nb_u, nb, stream)
-              : launch_fused_t<SS, false, false>(p, nb_t, nb_u, nb, stream);
+    if (p.diag >= 2) return launch_fused_t<SS, 2>(p, G, stream, launches);
+    if (p.diag == 1) return launch_fused_t<SS, 1>(p, G, stream, launches);
+    return launch_fused_t<SS, 0>(p, G, stream, launches);
 }
 
 int launch_fused(const FusedPlan &p, cudaStream_t stream, int *launches)
 {
-    const int nb_t = (p.do_early || p.do_normal) ? blocks_for(p.cells[0]) : 0;
-    const int nb_u = p.do_normal ? blocks_for(p.cells[1]) : 0;
-    const int nb_v = p.do_normal ? blocks_for(p.cells[2]) : 0;
-    const int nb = nb_t + nb_u + nb_v;
-    if (nb == 0) return 0;
-    const bool al = plan_aligned(p);
+    const FusedGeom G = fused_geometry(p);
+    if (G.nb_main + G.nb_tail == 0) return 0;
     cudaError_t e;
     switch (p.S) {
-        case 1: e = launch_fused_s<1>(p, nb_t, nb_u, nb, al, stream); break;
-        case 2: e = launch_fused_s<2>(p, nb_t, nb_u, nb, al, stream); break;
-        default: e = launch_fused_s<0>(p, nb_t, nb_u, nb, al, stream); break;
+        case 1: e = launch_fused_s<1>(p, G, stream, launches); break;
+        case 2: e = launch_fused_s<2>(p, G, stream, launches); break;
+        default: e = launch_fused_s<0>(p, G, stream, launches); break;
     }
-    if (launches) *launches += 1;
     return (int)e;
 }
 
-int launch_diag_finalize(const double *partials, int nblocks, int nslots, double *diag_out, cudaStream_t stream)
+// partials (written by the fused launches of `p`) -> diag_out[compact slot][3]
+int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cudaStream_t stream, int *launches)
 {
-    if (nslots <= 0) return 0;
-    diag_finalize_kernel<<<nslots, 256, 0, stream>>>(partials, nblocks, nslots, diag_out);
+    if (!p.diag || p.diag_n <= 0) return 0;
+    const FusedGeom G = fused_geometry(p);
+    const int w = kFusedThreads / 32;
+    DiagRanges R;
+    memset(&R, 0, sizeof R);
+    const int nbm[3] = {G.main.nb_t, G.main.nb_u, G.nb_main - G.main.nb_t - G.main.nb_u};
+    const int nbt[3] = {G.tail.nb_t, G.tail.nb_u, G.nb_tail - G.tail.nb_t - G.tail.nb_u};
+    int64_t rm = 0, rt = G.tail.row0;
+    for (int g = 0; g < 3; ++g) {
+        R.row_begin[g] = rm;
+        rm += (int64_t)nbm[g] * w;
+        R.row_end[g] = rm;
+        R.tail_begin[g] = rt;
+        rt += (int64_t)nbt[g] * w;
+        R.tail_end[g] = rt;
+    }
+    for (int s = 0; s < kDiagSlots; ++s) {
+        const int q = s % DQ_COUNT;
+        const int g = (q == DQ_QSUR_U || q == DQ_UMOM) ? 1 : ((q == DQ_QSUR_V || q == DQ_VMOM) ? 2 : 0);
+        if (p.diag_map[s] >= 0 && p.diag_map[s] < kDiagSlots) R.grid_of_slot[p.diag_map[s]] = (signed char)g;
+    }
+    const int64_t rows = p.diag_rows;
+    const int nchunks = (int)((rows + kDiagChunk - 1) / kDiagChunk);
+    const int planes = p.diag >= 2 ? 3 : 1;
+    diag_reduce_rows_kernel<<<dim3(nchunks, p.diag_n), 256, 0, stream>>>(p.diag_partials, rows, p.diag_n, planes, R, tmp, nchunks);
+    diag_reduce_final_kernel<<<p.diag_n, 256, 0, stream>>>(tmp, nchunks, planes, diag_out);
+    if (launches) *launches += 2;
     return (int)cudaGetLastError();
 }
+
+int diag_tmp_doubles(int64_t rows, int nslots) { return (int)(((rows + kDiagChunk - 1) / kDiagChunk) * nslots * 3); }
 
 int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t stream)
 {

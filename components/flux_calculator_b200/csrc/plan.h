@@ -116,9 +116,11 @@ struct FusedPlan {
     Consts c;
     FusedT t;
     FusedUV uv[2];           // [0] = u grid, [1] = v grid
-    double *diag_partials;   // [blocks][diag_n][3]
+    double *diag_partials;   // [plane: sum|min|max][diag_n][diag_rows]
+    int64_t diag_rows;       // warp rows of one fused step (row stride of the partials)
     int diag_n;              // number of active diagnostics slots
-    signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index (valid for active slots)
+    int prefetch_distance;   // L2 prefetch look-ahead in blocks (0 = off)
+    signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index, -1 = inactive
 };
 
 // diagnostics slot layout: slot(type 0..10, quantity)
@@ -126,16 +128,21 @@ enum DiagQuantity { DQ_QSUR_T = 0, DQ_MEVA, DQ_HLAT, DQ_HSEN, DQ_RBBR, DQ_RSDR, 
 constexpr int kDiagSlots = (kMaxSurfaceTypes + 1) * DQ_COUNT;
 
 constexpr int kFusedThreads = 256;
+#ifndef FC_MIN_BLOCKS
+#define FC_MIN_BLOCKS 2
+#endif
+constexpr int kFusedMinBlocks = FC_MIN_BLOCKS;               // __launch_bounds__ occupancy target
 constexpr int kFusedVec = 2;                                  // cells per thread (128-bit accesses)
 constexpr int kFusedCellsPerBlock = kFusedThreads * kFusedVec;
 
 // launchers (kernels.cu)
 int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t stream);
 int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
-int launch_diag_finalize(const double *partials, int nblocks, int nslots, double *diag_out, cudaStream_t stream);
+int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, cudaStream_t stream, int *launches);
+int64_t fused_diag_rows(const FusedPlan &plan);
+int diag_tmp_doubles(int64_t rows, int nslots);
 int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,
                       double *dst, int64_t n_dst, cudaStream_t stream);
-int fused_grid_blocks(const FusedPlan &plan);
 
 }  // namespace fc

@@ -260,7 +260,8 @@ int fc_kernel_time_ms(fc_context *ctx, double *total_ms, int64_t *count);
 
 /* options: "force_generic" (0/1: use the op-list interpreter kernels instead of the fused kernel),
  *          "pin_host" (0/1: cudaHostRegister bound host arrays), "h2d_chunks" (pipeline depth of the
- *          host-pointer path), "diagnostics" (0/1), "profile_kernel" (0/1) */
+ *          host-pointer path), "diagnostics" (0 off, 1 area-weighted sums, 2 sums + min/max),
+ *          "profile_kernel" (0/1) */
 int fc_set_option(fc_context *ctx, const char *name, int64_t value);
 int64_t fc_get_info(const fc_context *ctx, const char *name);
 /* info names: "launches" (kernel launches issued so far), "fused" (1 if the fused kernel serves
@@ -271,8 +272,9 @@ int64_t fc_get_info(const fc_context *ctx, const char *name);
  * Diagnostics (new, additive; reproduce the reference's debug "range =" lines, flux_calculator.F90:881,
  * :923,:951,:1013, plus area-weighted sums) and their multi-GPU reduction
  * ---------------------------------------------------------------------------------------------- */
-/* after a step with option diagnostics=1: out[0] = sum_j area_j * x_j, out[1] = min_j x_j,
- * out[2] = max_j x_j over the LOCAL cells (or over all ranks after fc_allreduce_diagnostics) */
+/* after a step with option diagnostics >= 1: out[0] = sum_j area_j * x_j; with diagnostics == 2 also
+ * out[1] = min_j x_j, out[2] = max_j x_j (NaN at level 1), over the LOCAL cells (or over all ranks after
+ * fc_allreduce_diagnostics) */
 int fc_get_diagnostics(fc_context *ctx, int surface_type, int grid, int var_idx, double out[3]);
 
 #define FC_UNIQUE_ID_BYTES 128

@@ -8,7 +8,7 @@ from tolerances import check_field
 pytestmark = pytest.mark.gpu
 
 
-def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chunks=None, diagnostics=False):
+def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chunks=None, diagnostics=0):
     from components.flux_calculator_b200 import DeviceArray
     # oracle
     o_in, o_out = sc.clone()
@@ -34,7 +34,7 @@ def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chu
     if diagnostics:
         for g in (1, 2, 3):
             fc.set_area(g, sc.area[g])
-        fc.set_option("diagnostics", 1)
+        fc.set_option("diagnostics", int(diagnostics))
     fc.prepare()
     if phases == "all":
         fc.step_all(t)
@@ -78,8 +78,10 @@ def test_generic_path_matches(fcmod, fset):
     compare(sc, o_out, g_out)
     fc2, _, f_out, _, _ = run_both(fcmod, sc, "device")
     assert fc2.info("fused") == 1
-    for k in g_out:     # fused and generic kernels agree bit for bit
-        assert np.array_equal(g_out[k], f_out[k], equal_nan=True), k
+    # fused (lock-step exp / exp(c*log x)) and generic (libdevice exp / pow) kernels: identical wherever no
+    # transcendental is upstream, within the stated tolerance elsewhere
+    for k in g_out:
+        check_field(k[2], f_out[k], g_out[k], fset)
 
 
 @pytest.mark.parametrize("S", [2, 3, 5])
@@ -140,13 +142,21 @@ def test_chunked_host_pipeline(fcmod):
         assert np.array_equal(g1[k], g7[k], equal_nan=True), k
 
 
-def test_diagnostics(fcmod):
+@pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("S,n", [(2, (10007, 10009, 10011)), (1, (200000, 150001, 99999)), (1, (3, 700, 0))])
+def test_diagnostics(fcmod, level, S, n):
     from components.flux_calculator_b200.synthetic import Scenario
-    sc = Scenario("CCLM", n=(10007, 10009, 10011), S=2, bias=True, averaging=True)
-    fc, o_out, g_out, _, _ = run_both(fcmod, sc, "device", diagnostics=True)
-    compare(sc, o_out, g_out)
-    for (i, g, name), arr in g_out.items():
-        s, mn, mx = fc.diagnostics(i, g, name)
-        assert mn == arr.min() and mx == arr.max(), (i, g, name)
-        ref = float(np.sum(sc.area[g] * arr))
-        assert abs(s - ref) <= 1e-11 * float(np.sum(np.abs(sc.area[g] * arr))), (i, g, name)
+    sc = Scenario("CCLM", n=n, S=S, bias=True, averaging=True)
+    for mode in ("device", "host"):
+        fc, o_out, g_out, _, _ = run_both(fcmod, sc, mode, diagnostics=level)
+        compare(sc, o_out, g_out)
+        for (i, g, name), arr in g_out.items():
+            if arr.size == 0:
+                continue
+            s, mn, mx = fc.diagnostics(i, g, name)
+            if level == 2:      # reproduces the reference's debug "range =" lines (flux_calculator.F90:1013)
+                assert mn == arr.min() and mx == arr.max(), (i, g, name)
+            else:
+                assert np.isnan(mn) and np.isnan(mx)
+            ref = float(np.sum(sc.area[g] * arr))
+            assert abs(s - ref) <= 1e-11 * float(np.sum(np.abs(sc.area[g] * arr))), (i, g, name)
