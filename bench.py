@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--diag", type=int, default=None, help="override the workload's diagnostics switch (0/1)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance in blocks (tuning)")
+    ap.add_argument("--staged", type=int, default=None, help="0/1: forbid/allow the staged kernel (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -220,6 +221,8 @@ def main():
         fc.set_option("diagnostics", 1)
     if args.prefetch is not None:
         fc.set_option("prefetch_distance", args.prefetch)
+    if args.staged is not None:
+        fc.set_option("staged", args.staged)
     fc.prepare()
     assert fc.info("fused") == 1, "bench workload must run on the fused kernel"
     if world > 1 and diag:
@@ -256,6 +259,7 @@ def main():
     kern_ms, kern_cnt = fc.kernel_time_ms()
     fc.set_option("profile_kernel", 0)
     launches = fc.info("launches") - launches0
+    exact_calls = fc.info("exact_path_calls")
     if dist:
         import torch
         t = torch.tensor([ms_total, kern_ms / max(kern_cnt, 1)], dtype=torch.float64)
@@ -373,7 +377,7 @@ def main():
                        "parallelism": "contiguous range per GPU (fc_shard_range), %d rank(s)" % world,
                        "l2": "inputs exceed L2 (%.0f MB per step per GPU vs 126 MB), no flush" % (bytes_per_cell * max_size / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "parity": parity, "diagnostics_sample": diag_sample,
+            "parity": parity, "diagnostics_sample": diag_sample, "exact_path_calls": exact_calls,
         }
         print(json.dumps(line))
     if dist:

@@ -461,6 +461,7 @@ extern "C" int fc_set_option(fc_context *c, const char *name, int64_t value)
     else if (!strcmp(name, "pin_host")) c->pin_host = value != 0;
     else if (!strcmp(name, "h2d_chunks")) c->h2d_chunks = (int)std::max<int64_t>(0, std::min<int64_t>(value, 256));
     else if (!strcmp(name, "diagnostics")) c->diagnostics = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
+    else if (!strcmp(name, "staged")) c->use_staged = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(name, "prefetch_distance")) c->prefetch_distance = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else if (!strcmp(name, "profile_kernel")) {
         c->profile_kernel = value != 0;
@@ -1131,6 +1132,51 @@ static bool build_fused(fc_context *c, bool do_early, bool do_normal, FusedBundl
         P.diag_n = (int)F.diag_slots.size();
         if (P.diag_n == 0) P.diag = 0;
     }
+    // stage lists of the staged kernel: the distinct input arrays of one tile, per grid
+    {
+        bool overflow = false;
+        for (int g = 0; g < 3; ++g) {
+            StageList &L = P.stage[g];
+            L.n = 0;
+            std::vector<const double *> seen;
+            auto add = [&](const double *ptr, signed char &slot) {
+                slot = -1;
+                if (!ptr) return;
+                for (size_t k = 0; k < seen.size(); ++k)
+                    if (seen[k] == ptr) {
+                        slot = (signed char)k;
+                        return;
+                    }
+                if (L.n >= kMaxStaged) {
+                    overflow = true;
+                    return;
+                }
+                slot = (signed char)L.n;
+                L.src[L.n++] = ptr;
+                seen.push_back(ptr);
+            };
+            if (g == 0) {
+                add(P.t.rsdd, P.t.s_rsdd);
+                add(P.t.bias, P.t.s_bias);
+                add(P.t.area, P.t.s_area);
+                for (int i = 0; i < c->S; ++i) {
+                    FusedTType &T = P.t.ty[i];
+                    add(T.fice, T.s_fice); add(T.psur, T.s_psur); add(T.tsur, T.s_tsur); add(T.qatm, T.s_qatm);
+                    add(T.tatm, T.s_tatm); add(T.patm, T.s_patm); add(T.uatm, T.s_uatm); add(T.vatm, T.s_vatm);
+                    add(T.a_evap, T.s_aev); add(T.a_sens, T.s_ase); add(T.qsur_in, T.s_qsur_in); add(T.fare, T.s_fare);
+                }
+            } else {
+                FusedUV &U = P.uv[g - 1];
+                add(U.area, U.s_area);
+                for (int i = 0; i < c->S; ++i) {
+                    FusedUVType &T = U.ty[i];
+                    add(T.fice, T.s_fice); add(T.psur, T.s_psur); add(T.tsur, T.s_tsur); add(T.a_mom, T.s_amom);
+                    add(T.uatm, T.s_uatm); add(T.vatm, T.s_vatm); add(T.qsur_in, T.s_qsur_in); add(T.fare, T.s_fare);
+                }
+            }
+        }
+        P.staged = overflow ? 0 : c->use_staged;
+    }
     F.in_bufs.assign(ins.begin(), ins.end());
     F.out_bufs.assign(outs.begin(), outs.end());
     F.ok = true;
@@ -1279,7 +1325,10 @@ static double *diag_tmp(fc_context *c, const FusedPlan &P)
 static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
 {
     FusedPlan P = F.plan;
-    if (P.t.bias) P.t.bias = bias_slab(c);
+    if (P.t.bias) {
+        P.t.bias = bias_slab(c);
+        if (P.t.s_bias >= 0) P.stage[0].src[P.t.s_bias] = P.t.bias;
+    }
     bool any_host = false;
     for (int b : F.in_bufs) any_host = any_host || !c->bufs[b].user_is_device;
     for (int b : F.out_bufs) any_host = any_host || !c->bufs[b].user_is_device;
@@ -1450,6 +1499,11 @@ extern "C" int64_t fc_get_info(const fc_context *c, const char *name)
 {
     if (!c || !name) return -1;
     if (!strcmp(name, "launches")) return c->launches;
+    if (!strcmp(name, "exact_path_calls")) {   // threads that recomputed their cells with the IEEE routines (process-wide)
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        return (int64_t)read_exact_calls();
+    }
     if (!strcmp(name, "fused")) return (!c->dirty && c->fused[2].ok) ? 1 : 0;
     if (!strcmp(name, "fused_early")) return (!c->dirty && c->fused[0].ok) ? 1 : 0;
     if (!strcmp(name, "fused_normal")) return (!c->dirty && c->fused[1].ok) ? 1 : 0;

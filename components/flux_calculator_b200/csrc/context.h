@@ -103,6 +103,7 @@ struct fc_context {
     bool pin_host = false;
     int diagnostics = 0;         // 0 off, 1 area-weighted sums, 2 sums + min/max
     int h2d_chunks = 0;          // 0 = auto
+    int use_staged = 1;          // staged (cp.async.bulk + mbarrier) kernel: 0 never, 1 for large grids, 2 whenever possible
     int prefetch_distance = 0;   // L2 prefetch look-ahead of the fused kernel, in 512-cell blocks (0 = off)
 
     // derived

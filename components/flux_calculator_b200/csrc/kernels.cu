@@ -14,6 +14,8 @@
 
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace fc {
 
@@ -25,47 +27,101 @@ using V2 = Vd<V>;
 using Fast = FastVec<V>;
 using Exact = ExactVec<V>;
 
-// FULL: all V cells of this thread are inside the grid and every array is 16-byte aligned -> one 128-bit
-// access; otherwise (last thread of a ragged grid, misaligned user pointers) guarded scalar accesses
-template <bool FULL>
-__device__ __forceinline__ V2 ldv(const double *__restrict__ p, int64_t j, int nv)
-{
-    V2 r;
-    if (FULL) {
+// Loader policies: where a thread's V cells of an input array come from, and how results are stored.
+//   LdGlobal : 128-bit global loads/stores (every array 16-byte aligned, all V cells valid)
+//   LdGuard  : guarded scalar accesses (ragged tail of a grid, misaligned arrays)
+//   LdStaged : inputs from the shared-memory stage a bulk copy (cp.async.bulk) filled, 128-bit global stores
+struct LdGlobal {
+    static constexpr bool kFull = true;
+    static constexpr bool kLazy = false;
+    int64_t j;
+    __device__ __forceinline__ V2 load(const double *__restrict__ p, int) const
+    {
         static_assert(V == 2, "128-bit path assumes 2 cells per thread");
         const double2 t = __ldg(reinterpret_cast<const double2 *>(p + j));
+        V2 r;
         r.v[0] = t.x;
         r.v[1] = t.y;
-    } else {
+        return r;
+    }
+    __device__ __forceinline__ void store(double *p, const V2 &x) const
+    {
+        *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
+    }
+    __device__ __forceinline__ void release() const {}
+};
+
+struct LdGuard {
+    static constexpr bool kFull = false;
+    static constexpr bool kLazy = false;
+    int64_t j;
+    int nv;
+    __device__ __forceinline__ V2 load(const double *__restrict__ p, int) const
+    {
+        V2 r;
 #pragma unroll
         for (int k = 0; k < V; ++k) r.v[k] = (k < nv) ? __ldg(p + j + k) : 1.0;
+        return r;
     }
-    return r;
-}
-
-template <bool FULL>
-__device__ __forceinline__ void stv(double *p, int64_t j, int nv, const V2 &x)
-{
-    if (FULL) {
-        *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
-    } else {
+    __device__ __forceinline__ void store(double *p, const V2 &x) const
+    {
 #pragma unroll
         for (int k = 0; k < V; ++k)
             if (k < nv) p[j + k] = x.v[k];
     }
-}
+    __device__ __forceinline__ void release() const {}
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar);
+
+constexpr int kStageSlotBytes = kFusedCellsPerBlock * 8;      // one array of one tile
+struct LdStaged {
+    static constexpr bool kFull = true;
+    static constexpr bool kLazy = true;
+    int64_t j;
+    const char *stage;      // this thread's 16 bytes of slot 0
+    uint64_t *empty;        // "stage may be refilled" barrier
+    // called by the chain right after its last read of the stage: the inputs now live in registers, so the
+    // producer can refill this stage while the arithmetic runs (keeps >= 1 tile per CTA in flight at all times)
+    __device__ __forceinline__ void release() const
+    {
+#ifdef FC_EARLY_RELEASE
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
+#endif
+    }
+    __device__ __forceinline__ void release_at_end() const
+    {
+#ifndef FC_EARLY_RELEASE
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
+#endif
+    }
+    __device__ __forceinline__ V2 load(const double *, int slot) const
+    {
+        const double2 t = *reinterpret_cast<const double2 *>(stage + slot * kStageSlotBytes);
+        V2 r;
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+        return r;
+    }
+    __device__ __forceinline__ void store(double *p, const V2 &x) const
+    {
+        *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
+    }
+};
 
 // a field loaded at most once per distinct pointer: atmosphere fields are aliased into every
 // surface type (distribute_input_field, basic.F90:334-358), so consecutive types usually share them
-template <bool FULL>
+template <class LD>
 struct Cached {
     const double *ptr = nullptr;
     V2 val;
-    __device__ __forceinline__ const V2 &get(const double *p, int64_t j, int nv)
+    __device__ __forceinline__ const V2 &get(const LD &ld, const double *p, int slot)
     {
         if (p != ptr) {
             ptr = p;
-            if (p) val = ldv<FULL>(p, j, nv);
+            if (p) val = ld.load(p, slot);
         }
         return val;
     }
@@ -97,11 +153,22 @@ struct DiagCtx {
     int64_t rows;        // row stride (total warp rows of the launch)
     int64_t row;         // this warp's row
     int64_t plane;       // slots * rows
+    double acc[DQ_COUNT];   // DIAG == 3: this thread's running sums (persistent staged kernel, S == 1)
 };
 
+// DIAG == 3 (staged kernel, sums only, one surface type): the thread just accumulates; the warp tree and the store
+// happen once per kernel instead of once per tile
 template <int DIAG>
-__device__ __forceinline__ void diag_commit(const FusedPlan &p, const DiagCtx &d, int slot, const V2 &x, const V2 &area, int nv)
+__device__ __forceinline__ void diag_commit(const FusedPlan &p, DiagCtx &d, int base, int q, const V2 &x, const V2 &area, int nv)
 {
+    if (DIAG == 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < V; ++k) s = add(s, mul(area.v[k], x.v[k]));
+        d.acc[q] = add(d.acc[q], s);
+        return;
+    }
+    const int slot = base + q;
     double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
 #pragma unroll
     for (int k = 0; k < V; ++k)
@@ -129,38 +196,88 @@ __device__ __forceinline__ void diag_commit(const FusedPlan &p, const DiagCtx &d
         }
     }
 }
-#define DIAG_COMMIT(slot, x) diag_commit<DIAG>(p, dg, (slot), (x), area, nv)
+#define DIAG_COMMIT(base, q, x) diag_commit<DIAG>(p, dg, (base), (q), (x), area, nv)
 
 // ---------------------------------------------------------------------------------------------
 // per-surface-type arithmetic of the t grid, instantiated with the fast and the exact policy
 // ---------------------------------------------------------------------------------------------
+// inputs of one surface type: preloaded into registers (direct-load kernels) ...
 struct TIn {
-    V2 fice, psur, tsur, qatm, tatm, patm, uatm, vatm, aev, ase, qsur_in, bias;
+    V2 fice_, psur_, tsur_, qatm_, tatm_, patm_, uatm_, vatm_, aev_, ase_, qsur_in_, bias_;
+    __device__ __forceinline__ const V2 &fice() const { return fice_; }
+    __device__ __forceinline__ const V2 &psur() const { return psur_; }
+    __device__ __forceinline__ const V2 &tsur() const { return tsur_; }
+    __device__ __forceinline__ const V2 &qatm() const { return qatm_; }
+    __device__ __forceinline__ const V2 &tatm() const { return tatm_; }
+    __device__ __forceinline__ const V2 &patm() const { return patm_; }
+    __device__ __forceinline__ const V2 &uatm() const { return uatm_; }
+    __device__ __forceinline__ const V2 &vatm() const { return vatm_; }
+    __device__ __forceinline__ const V2 &aev() const { return aev_; }
+    __device__ __forceinline__ const V2 &ase() const { return ase_; }
+    __device__ __forceinline__ const V2 &qsur_in() const { return qsur_in_; }
+    __device__ __forceinline__ const V2 &bias() const { return bias_; }
+};
+// ... or read from the shared-memory stage at the point of use (staged kernel): nothing is held in registers
+// longer than the expression that needs it, a re-read costs one LDS.128
+template <class LD>
+struct TInLazy {
+    const LD &ld;
+    const FusedTType &ty;
+    const FusedT &t;
+    __device__ __forceinline__ V2 fice() const { return ld.load(ty.fice, ty.s_fice); }
+    __device__ __forceinline__ V2 psur() const { return ld.load(ty.psur, ty.s_psur); }
+    __device__ __forceinline__ V2 tsur() const { return ld.load(ty.tsur, ty.s_tsur); }
+    __device__ __forceinline__ V2 qatm() const { return ld.load(ty.qatm, ty.s_qatm); }
+    __device__ __forceinline__ V2 tatm() const { return ld.load(ty.tatm, ty.s_tatm); }
+    __device__ __forceinline__ V2 patm() const { return ld.load(ty.patm, ty.s_patm); }
+    __device__ __forceinline__ V2 uatm() const { return ld.load(ty.uatm, ty.s_uatm); }
+    __device__ __forceinline__ V2 vatm() const { return ld.load(ty.vatm, ty.s_vatm); }
+    __device__ __forceinline__ V2 aev() const { return ld.load(ty.a_evap, ty.s_aev); }
+    __device__ __forceinline__ V2 ase() const { return ld.load(ty.a_sens, ty.s_ase); }
+    __device__ __forceinline__ V2 qsur_in() const { return ld.load(ty.qsur_in, ty.s_qsur_in); }
+    __device__ __forceinline__ V2 bias() const { return ld.load(t.bias, t.s_bias); }
+    __device__ __forceinline__ TIn materialize() const     // cold path only: unstaged (null) fields stay unset
+    {
+        TIn in;
+        if (ty.s_fice >= 0) in.fice_ = fice();
+        if (ty.s_psur >= 0) in.psur_ = psur();
+        if (ty.s_tsur >= 0) in.tsur_ = tsur();
+        if (ty.s_qatm >= 0) in.qatm_ = qatm();
+        if (ty.s_tatm >= 0) in.tatm_ = tatm();
+        if (ty.s_patm >= 0) in.patm_ = patm();
+        if (ty.s_uatm >= 0) in.uatm_ = uatm();
+        if (ty.s_vatm >= 0) in.vatm_ = vatm();
+        if (ty.s_aev >= 0) in.aev_ = aev();
+        if (ty.s_ase >= 0) in.ase_ = ase();
+        if (ty.s_qsur_in >= 0) in.qsur_in_ = qsur_in();
+        if (t.s_bias >= 0) in.bias_ = bias();
+        return in;
+    }
 };
 struct TOut {
     V2 qsur, meva, hlat, hsen, rbbr;
 };
 
-template <class M>
-__device__ __forceinline__ bool t_type_math(const FusedPlan &p, const FusedTType &ty, const TIn &in, bool has_bias, TOut &o)
+template <class M, class IN>
+__device__ __forceinline__ bool t_type_math(const FusedPlan &p, const FusedTType &ty, const IN &in, bool has_bias, TOut &o)
 {
     M m;
     const Consts &c = p.c;
     if (p.do_normal) {
         // --- QSUR: calc_spec_vapor_surface (calculate.F90:25-50)
-        if (ty.m_qsur == M_CCLM) o.qsur = spec_vapor_surface_cclm(m, in.fice, in.psur, in.tsur, c);
-        else o.qsur = in.qsur_in;
+        if (ty.m_qsur == M_CCLM) o.qsur = spec_vapor_surface_cclm(m, in.fice(), in.psur(), in.tsur(), c);
+        else if (ty.qsur_in) o.qsur = in.qsur_in();
         V2 vel;
-        if (ty.m_meva >= M_CCLM || ty.m_hsen >= M_CCLM) vel = wind_speed(m, in.uatm, in.vatm);
+        if (ty.m_meva >= M_CCLM || ty.m_hsen >= M_CCLM) vel = wind_speed(m, in.uatm(), in.vatm());
         // --- MEVA: calc_flux_mass_evap (calculate.F90:54-120); T slot <- TATM (:87,:98)
         if (ty.m_meva != M_NONE) {
             if (ty.m_meva == M_CCLM || ty.m_meva == M_MOM5)
-                o.meva = flux_mass_evap_cclm(m, in.aev, in.psur, in.qatm, o.qsur, in.tatm, vel, c);
+                o.meva = flux_mass_evap_cclm(m, in.aev(), in.psur(), in.qatm(), o.qsur, in.tatm(), vel, c);
             else if (ty.m_meva == M_RCO)
-                o.meva = flux_mass_evap_rco(m, in.qatm, in.tsur, vel);
+                o.meva = flux_mass_evap_rco(m, in.qatm(), in.tsur(), vel);
             else
                 o.meva = vzero();                                              // 'zero' (:79)
-            if (has_bias) o.meva = M::add(o.meva, in.bias);                    // :112-116
+            if (has_bias) o.meva = M::add(o.meva, in.bias());                    // :112-116
         }
         // --- HLAT: calc_flux_heat_latent (calculate.F90:124-154), sees the corrected MEVA
         if (ty.m_hlat != M_NONE)
@@ -168,70 +285,90 @@ __device__ __forceinline__ bool t_type_math(const FusedPlan &p, const FusedTType
         // --- HSEN: calc_flux_heat_sensible (calculate.F90:156-208); q_s slot <- QATM (:178,:190)
         if (ty.m_hsen != M_NONE) {
             if (ty.m_hsen == M_CCLM || ty.m_hsen == M_MOM5)
-                o.hsen = flux_heat_sensible_cclm(m, in.ase, in.patm, in.psur, in.qatm, in.tatm, in.tsur, vel, c);
+                o.hsen = flux_heat_sensible_cclm(m, in.ase(), in.patm(), in.psur(), in.qatm(), in.tatm(), in.tsur(), vel, c);
             else if (ty.m_hsen == M_RCO)
-                o.hsen = flux_heat_sensible_rco<M>(in.tatm, in.tsur, vel);
+                o.hsen = flux_heat_sensible_rco<M>(in.tatm(), in.tsur(), vel);
             else
                 o.hsen = vzero();
         }
     }
     // --- RBBR: calc_flux_radiation_blackbody (calculate.F90:320-345), early phase
     if (p.do_early && ty.m_rbbr != M_NONE)
-        o.rbbr = (ty.m_rbbr == M_ZERO) ? vzero() : flux_radiation_blackbody_StBo<M>(in.tsur, c.stefan_boltzmann_constant);
+        o.rbbr = (ty.m_rbbr == M_ZERO) ? vzero() : flux_radiation_blackbody_StBo<M>(in.tsur(), c.stefan_boltzmann_constant);
     return m.bad();
 }
 
-// recompute path (an operand left the range in which the lock-step sequences are proven): out of line, cold
-__device__ __noinline__ void t_type_exact(const FusedPlan &p, const FusedTType &ty, const TIn &in, bool has_bias, TOut &o)
+// how often the recompute path ran (per thread = per V cells); fc_get_info("exact_path_calls")
+__device__ unsigned long long g_exact_calls = 0ull;
+
+unsigned long long read_exact_calls()
 {
-    t_type_math<Exact>(p, ty, in, has_bias, o);
+    unsigned long long v = 0;
+    cudaMemcpyFromSymbol(&v, g_exact_calls, sizeof v);
+    return v;
 }
 
-template <int SS, int DIAG, bool FULL>
-__device__ __forceinline__ void t_chain(const FusedPlan &p, int64_t j, int nv, const DiagCtx &dg)
+// recompute path (an operand left the range in which the lock-step sequences are proven): out of line, cold
+// (arguments and result by value: taking the address of the caller's register-resident structs would force
+// them into local memory on the hot path as well)
+__device__ __noinline__ TOut t_type_exact(const FusedPlan &p, int type_index, TIn in, bool has_bias)
+{
+    TOut o;
+    atomicAdd(&g_exact_calls, 1ull);
+    t_type_math<Exact>(p, p.t.ty[type_index], in, has_bias, o);
+    return o;
+}
+
+template <int SS, int DIAG, class LD>
+__device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv, DiagCtx &dg)
 {
     const FusedT &t = p.t;
     const int S = SS ? SS : p.S;
-    Cached<FULL> cPSUR, cQATM, cTATM, cPATM, cUATM, cVATM, cAEV, cASE, cFICE, cTSUR;
+    Cached<LD> cPSUR, cQATM, cTATM, cPATM, cUATM, cVATM, cAEV, cASE, cFICE, cTSUR;
     TIn in;
     V2 rsdd, area;
     const bool has_bias = p.do_normal && t.bias != nullptr;
     const bool has_rsdr = p.do_normal && t.rsdd != nullptr;
-    if (has_bias) in.bias = ldv<FULL>(t.bias, j, nv);
-    if (has_rsdr) rsdd = ldv<FULL>(t.rsdd, j, nv);
-    if (DIAG) area = ldv<FULL>(t.area, j, nv);
+    if (has_bias && !LD::kLazy) in.bias_ = ld.load(t.bias, t.s_bias);
+    if (has_rsdr) rsdd = ld.load(t.rsdd, t.s_rsdd);
+    if (DIAG) area = ld.load(t.area, t.s_area);
     V2 aQ = vzero(), aM = vzero(), aL = vzero(), aH = vzero(), aR = vzero(), aS = vzero();   // type-0 averages
 
     auto per_type = [&](const int i) {
         const FusedTType &ty = t.ty[i];
         V2 fare;
         TOut o;
-        if (FULL || nv) {
+        if (LD::kFull || nv) {
             // all loads of this surface type up front (memory-level parallelism), then arithmetic
-            in.tsur = cTSUR.get(ty.tsur, j, nv);
-            if (ty.fare) fare = ldv<FULL>(ty.fare, j, nv);
-            if (p.do_normal) {
-                in.psur = cPSUR.get(ty.psur, j, nv);
-                in.qatm = cQATM.get(ty.qatm, j, nv);
-                in.tatm = cTATM.get(ty.tatm, j, nv);
-                in.uatm = cUATM.get(ty.uatm, j, nv);
-                in.vatm = cVATM.get(ty.vatm, j, nv);
-                in.fice = cFICE.get(ty.fice, j, nv);
-                in.aev = cAEV.get(ty.a_evap, j, nv);
-                in.ase = cASE.get(ty.a_sens, j, nv);
-                in.patm = cPATM.get(ty.patm, j, nv);
-                if (ty.qsur_in) in.qsur_in = ldv<FULL>(ty.qsur_in, j, nv);
+            if (ty.fare) fare = ld.load(ty.fare, ty.s_fare);
+            if constexpr (LD::kLazy) {
+                const TInLazy<LD> lin{ld, ty, t};
+                if (t_type_math<Fast>(p, ty, lin, has_bias, o)) o = t_type_exact(p, i, lin.materialize(), has_bias);
+            } else {
+                in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
+                if (p.do_normal) {
+                    in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
+                    in.qatm_ = cQATM.get(ld, ty.qatm, ty.s_qatm);
+                    in.tatm_ = cTATM.get(ld, ty.tatm, ty.s_tatm);
+                    in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
+                    in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
+                    in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
+                    in.aev_ = cAEV.get(ld, ty.a_evap, ty.s_aev);
+                    in.ase_ = cASE.get(ld, ty.a_sens, ty.s_ase);
+                    in.patm_ = cPATM.get(ld, ty.patm, ty.s_patm);
+                    if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
+                }
+                if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
+                    o = t_type_exact(p, i, in, has_bias);             // redo these cells with the IEEE routines
             }
-            if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
-                t_type_exact(p, ty, in, has_bias, o);             // redo these cells with the IEEE routines
             if (p.do_normal) {
-                if (ty.m_qsur == M_CCLM) stv<FULL>(ty.qsur, j, nv, o.qsur);
-                if (ty.m_meva != M_NONE) stv<FULL>(ty.meva, j, nv, o.meva);
-                if (ty.m_hlat != M_NONE) stv<FULL>(ty.hlat, j, nv, o.hlat);
-                if (ty.m_hsen != M_NONE) stv<FULL>(ty.hsen, j, nv, o.hsen);
-                if (has_rsdr) stv<FULL>(ty.rsdr, j, nv, rsdd);                 // calculate.F90:347-364
+                if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
+                if (ty.m_meva != M_NONE) ld.store(ty.meva, o.meva);
+                if (ty.m_hlat != M_NONE) ld.store(ty.hlat, o.hlat);
+                if (ty.m_hsen != M_NONE) ld.store(ty.hsen, o.hsen);
+                if (has_rsdr) ld.store(ty.rsdr, rsdd);                 // calculate.F90:347-364
             }
-            if (p.do_early && ty.m_rbbr != M_NONE) stv<FULL>(ty.rbbr, j, nv, o.rbbr);
+            if (p.do_early && ty.m_rbbr != M_NONE) ld.store(ty.rbbr, o.rbbr);
             if (t.avg_qsur) avg_acc(aQ, o.qsur, fare);
             if (t.avg_meva) avg_acc(aM, o.meva, fare);
             if (t.avg_hlat) avg_acc(aL, o.hlat, fare);
@@ -242,13 +379,13 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, int64_t j, int nv, c
         if (DIAG) {
             const int base = (i + 1) * DQ_COUNT;
             if (p.do_normal) {
-                if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base + DQ_QSUR_T, o.qsur);
-                if (ty.m_meva != M_NONE) DIAG_COMMIT(base + DQ_MEVA, o.meva);
-                if (ty.m_hlat != M_NONE) DIAG_COMMIT(base + DQ_HLAT, o.hlat);
-                if (ty.m_hsen != M_NONE) DIAG_COMMIT(base + DQ_HSEN, o.hsen);
-                if (has_rsdr) DIAG_COMMIT(base + DQ_RSDR, rsdd);
+                if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base, DQ_QSUR_T, o.qsur);
+                if (ty.m_meva != M_NONE) DIAG_COMMIT(base, DQ_MEVA, o.meva);
+                if (ty.m_hlat != M_NONE) DIAG_COMMIT(base, DQ_HLAT, o.hlat);
+                if (ty.m_hsen != M_NONE) DIAG_COMMIT(base, DQ_HSEN, o.hsen);
+                if (has_rsdr) DIAG_COMMIT(base, DQ_RSDR, rsdd);
             }
-            if (p.do_early && ty.m_rbbr != M_NONE) DIAG_COMMIT(base + DQ_RBBR, o.rbbr);
+            if (p.do_early && ty.m_rbbr != M_NONE) DIAG_COMMIT(base, DQ_RBBR, o.rbbr);
         }
     };
     if constexpr (SS > 0) {
@@ -258,21 +395,21 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, int64_t j, int nv, c
 #pragma unroll 1
         for (int i = 0; i < S; ++i) per_type(i);
     }
-    if (FULL || nv) {
-        if (t.avg_qsur) stv<FULL>(t.avg_qsur, j, nv, aQ);
-        if (t.avg_meva) stv<FULL>(t.avg_meva, j, nv, aM);
-        if (t.avg_hlat) stv<FULL>(t.avg_hlat, j, nv, aL);
-        if (t.avg_hsen) stv<FULL>(t.avg_hsen, j, nv, aH);
-        if (t.avg_rbbr) stv<FULL>(t.avg_rbbr, j, nv, aR);
-        if (t.avg_rsdr) stv<FULL>(t.avg_rsdr, j, nv, aS);
+    if (LD::kFull || nv) {
+        if (t.avg_qsur) ld.store(t.avg_qsur, aQ);
+        if (t.avg_meva) ld.store(t.avg_meva, aM);
+        if (t.avg_hlat) ld.store(t.avg_hlat, aL);
+        if (t.avg_hsen) ld.store(t.avg_hsen, aH);
+        if (t.avg_rbbr) ld.store(t.avg_rbbr, aR);
+        if (t.avg_rsdr) ld.store(t.avg_rsdr, aS);
     }
     if (DIAG) {
-        if (t.avg_qsur) DIAG_COMMIT(DQ_QSUR_T, aQ);
-        if (t.avg_meva) DIAG_COMMIT(DQ_MEVA, aM);
-        if (t.avg_hlat) DIAG_COMMIT(DQ_HLAT, aL);
-        if (t.avg_hsen) DIAG_COMMIT(DQ_HSEN, aH);
-        if (t.avg_rbbr) DIAG_COMMIT(DQ_RBBR, aR);
-        if (t.avg_rsdr) DIAG_COMMIT(DQ_RSDR, aS);
+        if (t.avg_qsur) DIAG_COMMIT(0, DQ_QSUR_T, aQ);
+        if (t.avg_meva) DIAG_COMMIT(0, DQ_MEVA, aM);
+        if (t.avg_hlat) DIAG_COMMIT(0, DQ_HLAT, aL);
+        if (t.avg_hsen) DIAG_COMMIT(0, DQ_HSEN, aH);
+        if (t.avg_rbbr) DIAG_COMMIT(0, DQ_RBBR, aR);
+        if (t.avg_rsdr) DIAG_COMMIT(0, DQ_RSDR, aS);
     }
 }
 
@@ -280,74 +417,117 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, int64_t j, int nv, c
 // u / v grid
 // ---------------------------------------------------------------------------------------------
 struct UVIn {
-    V2 fice, psur, tsur, amom, uatm, vatm, qsur_in;
+    V2 fice_, psur_, tsur_, amom_, uatm_, vatm_, qsur_in_;
+    __device__ __forceinline__ const V2 &fice() const { return fice_; }
+    __device__ __forceinline__ const V2 &psur() const { return psur_; }
+    __device__ __forceinline__ const V2 &tsur() const { return tsur_; }
+    __device__ __forceinline__ const V2 &amom() const { return amom_; }
+    __device__ __forceinline__ const V2 &uatm() const { return uatm_; }
+    __device__ __forceinline__ const V2 &vatm() const { return vatm_; }
+    __device__ __forceinline__ const V2 &qsur_in() const { return qsur_in_; }
+};
+template <class LD>
+struct UVInLazy {
+    const LD &ld;
+    const FusedUVType &ty;
+    __device__ __forceinline__ V2 fice() const { return ld.load(ty.fice, ty.s_fice); }
+    __device__ __forceinline__ V2 psur() const { return ld.load(ty.psur, ty.s_psur); }
+    __device__ __forceinline__ V2 tsur() const { return ld.load(ty.tsur, ty.s_tsur); }
+    __device__ __forceinline__ V2 amom() const { return ld.load(ty.a_mom, ty.s_amom); }
+    __device__ __forceinline__ V2 uatm() const { return ld.load(ty.uatm, ty.s_uatm); }
+    __device__ __forceinline__ V2 vatm() const { return ld.load(ty.vatm, ty.s_vatm); }
+    __device__ __forceinline__ V2 qsur_in() const { return ld.load(ty.qsur_in, ty.s_qsur_in); }
+    __device__ __forceinline__ UVIn materialize() const
+    {
+        UVIn in;
+        if (ty.s_fice >= 0) in.fice_ = fice();
+        if (ty.s_psur >= 0) in.psur_ = psur();
+        if (ty.s_tsur >= 0) in.tsur_ = tsur();
+        if (ty.s_amom >= 0) in.amom_ = amom();
+        if (ty.s_uatm >= 0) in.uatm_ = uatm();
+        if (ty.s_vatm >= 0) in.vatm_ = vatm();
+        if (ty.s_qsur_in >= 0) in.qsur_in_ = qsur_in();
+        return in;
+    }
 };
 struct UVOut {
     V2 qsur, mom;
 };
 
-template <class M>
-__device__ __forceinline__ bool uv_type_math(const FusedPlan &p, const FusedUVType &ty, const UVIn &in, int north, UVOut &o)
+template <class M, class IN>
+__device__ __forceinline__ bool uv_type_math(const FusedPlan &p, const FusedUVType &ty, const IN &in, int north, UVOut &o)
 {
     M m;
     const Consts &c = p.c;
     // --- QSUR on this grid (calculate.F90:25-50, called for grids 2 and 3)
-    if (ty.m_qsur == M_CCLM) o.qsur = spec_vapor_surface_cclm(m, in.fice, in.psur, in.tsur, c);
-    else o.qsur = in.qsur_in;
+    if (ty.m_qsur == M_CCLM) o.qsur = spec_vapor_surface_cclm(m, in.fice(), in.psur(), in.tsur(), c);
+    else if (ty.qsur_in) o.qsur = in.qsur_in();
     // --- momentum: calc_flux_momentum_east / _north (calculate.F90:212-316)
     if (ty.m_mom != M_NONE) {
         if (ty.m_mom == M_ZERO) {
             o.mom = vzero();
         } else {
-            const V2 vel = wind_speed(m, in.uatm, in.vatm);
+            const V2 vel = wind_speed(m, in.uatm(), in.vatm());
             const V2 fa = (ty.m_mom == M_RCO) ? momentum_flux_air_rco<M>(vel)
-                                              : momentum_flux_air_cclm(m, in.amom, in.psur, o.qsur, in.tsur, vel, c);
-            o.mom = momentum_component<M>(fa, north ? in.vatm : in.uatm);
+                                              : momentum_flux_air_cclm(m, in.amom(), in.psur(), o.qsur, in.tsur(), vel, c);
+            o.mom = momentum_component<M>(fa, north ? in.vatm() : in.uatm());
         }
     }
     return m.bad();
 }
 
-__device__ __noinline__ void uv_type_exact(const FusedPlan &p, const FusedUVType &ty, const UVIn &in, int north, UVOut &o)
+__device__ __noinline__ UVOut uv_type_exact(const FusedPlan &p, int which, int type_index, UVIn in)
 {
-    uv_type_math<Exact>(p, ty, in, north, o);
+    UVOut o;
+    atomicAdd(&g_exact_calls, 1ull);
+    const FusedUV &g = p.uv[which - 1];
+    uv_type_math<Exact>(p, g.ty[type_index], in, g.north, o);
+    return o;
 }
 
-template <int SS, int DIAG, bool FULL>
-__device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, int which, int64_t j, int nv, const DiagCtx &dg)
+template <int SS, int DIAG, class LD>
+__device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, int which, const LD &ld, int nv, DiagCtx &dg)
 {
     const int S = SS ? SS : p.S;
-    const int dq_q = (which == 1) ? DQ_QSUR_U : DQ_QSUR_V;
-    const int dq_m = (which == 1) ? DQ_UMOM : DQ_VMOM;
-    Cached<FULL> cPSUR, cUATM, cVATM, cAMOM, cFICE, cTSUR;
+    Cached<LD> cPSUR, cUATM, cVATM, cAMOM, cFICE, cTSUR;
     UVIn in;
     V2 area;
-    if (DIAG) area = ldv<FULL>(g.area, j, nv);
+    if (DIAG) area = ld.load(g.area, g.s_area);
     V2 aQ = vzero(), aM = vzero();
 
     auto per_type = [&](const int i) {
         const FusedUVType &ty = g.ty[i];
         V2 fare;
         UVOut o;
-        if (FULL || nv) {
-            if (ty.fare) fare = ldv<FULL>(ty.fare, j, nv);
-            in.fice = cFICE.get(ty.fice, j, nv);
-            in.psur = cPSUR.get(ty.psur, j, nv);
-            in.tsur = cTSUR.get(ty.tsur, j, nv);
-            in.uatm = cUATM.get(ty.uatm, j, nv);
-            in.vatm = cVATM.get(ty.vatm, j, nv);
-            in.amom = cAMOM.get(ty.a_mom, j, nv);
-            if (ty.qsur_in) in.qsur_in = ldv<FULL>(ty.qsur_in, j, nv);
-            if (uv_type_math<Fast>(p, ty, in, g.north, o)) uv_type_exact(p, ty, in, g.north, o);
-            if (ty.m_qsur == M_CCLM) stv<FULL>(ty.qsur, j, nv, o.qsur);
-            if (ty.m_mom != M_NONE) stv<FULL>(ty.mom, j, nv, o.mom);
+        if (LD::kFull || nv) {
+            if (ty.fare) fare = ld.load(ty.fare, ty.s_fare);
+            if constexpr (LD::kLazy) {
+                const UVInLazy<LD> lin{ld, ty};
+                if (uv_type_math<Fast>(p, ty, lin, g.north, o)) o = uv_type_exact(p, which, i, lin.materialize());
+            } else {
+                in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
+                in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
+                in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
+                in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
+                in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
+                in.amom_ = cAMOM.get(ld, ty.a_mom, ty.s_amom);
+                if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
+                if (uv_type_math<Fast>(p, ty, in, g.north, o)) o = uv_type_exact(p, which, i, in);
+            }
+            if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
+            if (ty.m_mom != M_NONE) ld.store(ty.mom, o.mom);
             if (g.avg_qsur) avg_acc(aQ, o.qsur, fare);
             if (g.avg_mom) avg_acc(aM, o.mom, fare);
         }
         if (DIAG) {
             const int base = (i + 1) * DQ_COUNT;
-            if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base + dq_q, o.qsur);
-            if (ty.m_mom != M_NONE) DIAG_COMMIT(base + dq_m, o.mom);
+            if (which == 1) {
+                if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base, DQ_QSUR_U, o.qsur);
+                if (ty.m_mom != M_NONE) DIAG_COMMIT(base, DQ_UMOM, o.mom);
+            } else {
+                if (ty.m_qsur == M_CCLM) DIAG_COMMIT(base, DQ_QSUR_V, o.qsur);
+                if (ty.m_mom != M_NONE) DIAG_COMMIT(base, DQ_VMOM, o.mom);
+            }
         }
     };
     if constexpr (SS > 0) {
@@ -357,13 +537,18 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
 #pragma unroll 1
         for (int i = 0; i < S; ++i) per_type(i);
     }
-    if (FULL || nv) {
-        if (g.avg_qsur) stv<FULL>(g.avg_qsur, j, nv, aQ);
-        if (g.avg_mom) stv<FULL>(g.avg_mom, j, nv, aM);
+    if (LD::kFull || nv) {
+        if (g.avg_qsur) ld.store(g.avg_qsur, aQ);
+        if (g.avg_mom) ld.store(g.avg_mom, aM);
     }
     if (DIAG) {
-        if (g.avg_qsur) DIAG_COMMIT(dq_q, aQ);
-        if (g.avg_mom) DIAG_COMMIT(dq_m, aM);
+        if (which == 1) {
+            if (g.avg_qsur) DIAG_COMMIT(0, DQ_QSUR_U, aQ);
+            if (g.avg_mom) DIAG_COMMIT(0, DQ_UMOM, aM);
+        } else {
+            if (g.avg_qsur) DIAG_COMMIT(0, DQ_QSUR_V, aQ);
+            if (g.avg_mom) DIAG_COMMIT(0, DQ_VMOM, aM);
+        }
     }
 }
 
@@ -457,9 +642,150 @@ fused_step_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ L
         dg.plane = (int64_t)p.diag_n * p.diag_rows;
         dg.row = geo.row0 + (int64_t)b * (kFusedThreads / 32) + (threadIdx.x >> 5);
     }
-    if (!DIAG && nv == 0) return;      // with DIAG even empty threads take part in the warp reductions
-    if (which == 0) t_chain<SS, DIAG, FULL>(p, j, FULL ? V : nv, dg);
-    else uv_chain<SS, DIAG, FULL>(p, p.uv[which - 1], which, j, FULL ? V : nv, dg);
+    if (FULL) {        // whole 512-cell blocks only: every thread owns V valid cells
+        const LdGlobal ld{j};
+        if (which == 0) t_chain<SS, DIAG>(p, ld, V, dg);
+        else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, V, dg);
+    } else {
+        if (!DIAG && nv == 0) return;      // with DIAG even empty threads take part in the warp reductions
+        const LdGuard ld{j, nv};
+        if (which == 0) t_chain<SS, DIAG>(p, ld, nv, dg);
+        else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, nv, dg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// staged variant: persistent CTAs, one producer warp streams the input arrays of 512-cell tiles into a ring of
+// shared-memory stages with cp.async.bulk (completion counted on an mbarrier), eight consumer warps run the
+// same chains reading their cells from shared memory.  The bytes in flight per SM are then set by the ring
+// (>= 48 KB per CTA), not by registers x resident warps -- ncu showed long_scoreboard as the dominant stall of
+// the direct-load kernel at 16 resident warps/SM, worst on the light u/v chains (2-6 loads per thread).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred P_OUT;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P_OUT, [%1], %2;\n\t"
+                 "selp.b32 %0, 1, 0, P_OUT;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+constexpr int kStagedConsumers = kFusedThreads;              // 8 consumer warps = one 512-cell tile
+constexpr int kStagedThreads = kStagedConsumers + 32;        // + 1 producer warp
+constexpr int kMaxStages = 8;
+
+struct StagedGeom {
+    int64_t first[3];        // first cell of the staged range on each grid
+    int ntiles[3];           // whole tiles per grid
+    int nstages;
+    int stage_bytes;
+    int64_t row0;            // first diagnostics row
+};
+
+template <int SS, int DIAG>
+__global__ void __launch_bounds__(kStagedThreads, 2)
+fused_step_staged_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ StagedGeom geo)
+{
+    extern __shared__ __align__(128) char stage_mem[];
+    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
+    const int NS = geo.nstages;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full_bar[s], 1);                          // one expect_tx arrival + the bytes
+            mbar_init(&empty_bar[s], kStagedConsumers / 32);     // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    const int total = geo.ntiles[0] + geo.ntiles[1] + geo.ntiles[2];
+    const int warp = threadIdx.x >> 5;
+    auto decode = [&](int tile, int &which, int64_t &cell) {
+        which = (tile < geo.ntiles[0]) ? 0 : (tile < geo.ntiles[0] + geo.ntiles[1] ? 1 : 2);
+        const int idx = (which == 0) ? tile : (which == 1 ? tile - geo.ntiles[0] : tile - geo.ntiles[0] - geo.ntiles[1]);
+        cell = geo.first[which] + (int64_t)idx * kFusedCellsPerBlock;
+    };
+    if (warp == kStagedConsumers / 32) {
+        // ---------------- producer warp: one lane issues the bulk copies ----------------
+        if ((threadIdx.x & 31) == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+                const int s = it % NS;
+                if (it >= NS) mbar_wait(&empty_bar[s], ((it / NS) - 1) & 1);
+                int which;
+                int64_t cell;
+                decode(tile, which, cell);
+                const StageList &L = p.stage[which];
+                mbar_expect_tx(&full_bar[s], (uint32_t)L.n * kStageSlotBytes);
+                char *dst = stage_mem + (size_t)s * geo.stage_bytes;
+                for (int a = 0; a < L.n; ++a) bulk_g2s(dst + a * kStageSlotBytes, L.src[a] + cell, kStageSlotBytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+    // ---------------- consumer warps ----------------
+    DiagCtx dg;
+    if (DIAG) {
+        dg.base = p.diag_partials;
+        dg.rows = p.diag_rows;
+        dg.plane = (int64_t)p.diag_n * p.diag_rows;
+#pragma unroll
+        for (int q = 0; q < DQ_COUNT; ++q) dg.acc[q] = 0.0;
+    }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int s = it % NS;
+        int which;
+        int64_t cell;
+        decode(tile, which, cell);
+        mbar_wait(&full_bar[s], (it / NS) & 1);
+        const LdStaged ld{cell + (int64_t)threadIdx.x * V, stage_mem + (size_t)s * geo.stage_bytes + threadIdx.x * (V * 8),
+                          &empty_bar[s]};
+        if (DIAG) dg.row = geo.row0 + (int64_t)tile * (kStagedConsumers / 32) + warp;
+        if (which == 0) t_chain<SS, DIAG>(p, ld, V, dg);
+        else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, V, dg);
+        ld.release_at_end();      // stage s may be refilled
+    }
+    if (DIAG == 3) {
+        // one warp tree + one store per field for the whole kernel; row = this consumer warp
+        const int64_t row = geo.row0 + (int64_t)blockIdx.x * (kStagedConsumers / 32) + warp;
+#pragma unroll
+        for (int q = 0; q < DQ_COUNT; ++q) {
+            const int cs = p.diag_map[DQ_COUNT + q];      // surface type 1
+            if (cs < 0) continue;
+            double v = dg.acc[q];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = add(v, __shfl_down_sync(0xffffffffu, v, off));
+            if ((threadIdx.x & 31) == 0) p.diag_partials[(int64_t)cs * p.diag_rows + row] = v;
+        }
+    }
 }
 
 // diagnostics reduction, deterministic (fixed tree, independent of scheduling):
@@ -667,12 +993,28 @@ static bool plan_aligned(const FusedPlan &p)
     return a;
 }
 
-// geometry of the (up to) two launches of one fused step: whole 512-cell blocks through the 128-bit kernel,
-// the ragged remainder (or everything, if an array is misaligned) through the guarded kernel
+// geometry of the (up to) two launches of one fused step: whole 512-cell blocks through the 128-bit kernel
+// (staged or direct), the ragged remainder (or everything, if an array is misaligned) through the guarded kernel
 struct FusedGeom {
     LaunchGeom main, tail;
     int nb_main, nb_tail;
+    bool staged;
+    bool diag_accum;     // staged kernel accumulates the diagnostics per thread: one row per consumer warp of the grid
+    StagedGeom sg;
+    int staged_grid;
+    size_t staged_smem;
 };
+
+static int num_sms()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
 
 static FusedGeom fused_geometry(const FusedPlan &p)
 {
@@ -701,20 +1043,74 @@ static FusedGeom fused_geometry(const FusedPlan &p)
     G.tail.row0 = (int64_t)G.nb_main * (kFusedThreads / 32);
     G.main.prefetch_distance = p.prefetch_distance;
     G.tail.prefetch_distance = 0;
+    // staged variant: surface-type-static kernels only (S == 1), every active grid staged, >= 2 stages per CTA
+    G.staged = false;
+    if (p.S == 1 && ((p.staged == 1 && G.nb_main >= 4 * num_sms()) || (p.staged == 2 && G.nb_main > 0))) {   // small grids: direct kernel
+        int nmax = 0;
+        bool ok = true;
+        for (int g = 0; g < 3; ++g)
+            if (nbm[g] > 0) {
+                ok = ok && p.stage[g].n > 0;
+                nmax = p.stage[g].n > nmax ? p.stage[g].n : nmax;
+            }
+        const int budget = 110 * 1024;      // two CTAs per SM share 227 KB
+        const int stage_bytes = nmax * kStageSlotBytes;
+        const int ns = (ok && stage_bytes > 0) ? budget / stage_bytes : 0;
+        if (ns >= 2) {
+            G.staged = true;
+            for (int g = 0; g < 3; ++g) {
+                G.sg.first[g] = G.main.first[g];
+                G.sg.ntiles[g] = nbm[g];
+            }
+            G.sg.nstages = ns > kMaxStages ? kMaxStages : ns;
+            G.sg.stage_bytes = stage_bytes;
+            G.sg.row0 = 0;
+            G.staged_smem = (size_t)G.sg.nstages * stage_bytes;
+            const int cap = 2 * num_sms();
+            G.staged_grid = G.nb_main < cap ? G.nb_main : cap;
+            G.diag_accum = (p.diag == 1);
+            if (G.diag_accum) G.tail.row0 = (int64_t)G.staged_grid * (kFusedThreads / 32);
+        }
+    }
     return G;
 }
 
 int64_t fused_diag_rows(const FusedPlan &p)
 {
     const FusedGeom G = fused_geometry(p);
-    return (int64_t)(G.nb_main + G.nb_tail) * (kFusedThreads / 32);
+    return G.tail.row0 + (int64_t)G.nb_tail * (kFusedThreads / 32);
+}
+
+template <int SS, int DIAG>
+static cudaError_t launch_staged(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream)
+{
+    static size_t configured = 0;
+    if (G.staged_smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_step_staged_kernel<SS, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)G.staged_smem);
+        if (e != cudaSuccess) return e;
+        // two CTAs per SM must fit: ask for the largest shared-memory carveout
+        e = cudaFuncSetAttribute(fused_step_staged_kernel<SS, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured = G.staged_smem;
+    }
+    // persistent grid: two CTAs per SM (they fit by construction: <= 110 KB of stages each); if fewer were
+    // resident the kernel would still be correct, the persistent loop strides by gridDim
+    fused_step_staged_kernel<SS, DIAG><<<G.staged_grid, kStagedThreads, G.staged_smem, stream>>>(p, G.sg);
+    return cudaGetLastError();
 }
 
 template <int SS, int DIAG>
 static cudaError_t launch_fused_t(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream, int *launches)
 {
     if (G.nb_main) {
-        fused_step_kernel<SS, DIAG, true><<<G.nb_main, kFusedThreads, 0, stream>>>(p, G.main);
+        if (SS == 1 && G.staged) {
+            cudaError_t e = (DIAG == 1) ? launch_staged<1, 3>(p, G, stream) : launch_staged<1, DIAG>(p, G, stream);
+            if (e != cudaSuccess) return e;
+        } else {
+            fused_step_kernel<SS, DIAG, true><<<G.nb_main, kFusedThreads, 0, stream>>>(p, G.main);
+        }
         if (launches) *launches += 1;
     }
     if (G.nb_tail) {
@@ -757,9 +1153,14 @@ int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cuda
     const int nbt[3] = {G.tail.nb_t, G.tail.nb_u, G.nb_tail - G.tail.nb_t - G.tail.nb_u};
     int64_t rm = 0, rt = G.tail.row0;
     for (int g = 0; g < 3; ++g) {
-        R.row_begin[g] = rm;
-        rm += (int64_t)nbm[g] * w;
-        R.row_end[g] = rm;
+        if (G.diag_accum) {       // every consumer warp of the persistent grid holds sums of all three grids
+            R.row_begin[g] = 0;
+            R.row_end[g] = (int64_t)G.staged_grid * w;
+        } else {
+            R.row_begin[g] = rm;
+            rm += (int64_t)nbm[g] * w;
+            R.row_end[g] = rm;
+        }
         R.tail_begin[g] = rt;
         rt += (int64_t)nbt[g] * w;
         R.tail_end[g] = rt;

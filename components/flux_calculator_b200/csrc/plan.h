@@ -70,6 +70,8 @@ struct OpList {
 // ---------------------------------------------------------------------------------------------
 // fused plan
 // ---------------------------------------------------------------------------------------------
+// s_* = slot of that input array in the shared-memory stage of the staged kernel (-1: not staged); arrays
+// bound to several slots of the registry (aliases) share one stage slot
 struct FusedTType {     // one surface type on the t grid
     const double *fice, *psur, *tsur, *qatm, *tatm, *patm, *uatm, *vatm;
     const double *a_evap;    // AMOI (CCLM) or CMOI (MOM5)
@@ -79,12 +81,22 @@ struct FusedTType {     // one surface type on the t grid
     double *qsur, *meva, *hlat, *hsen, *rbbr, *rsdr;
     int m_qsur, m_meva, m_hlat, m_hsen, m_rbbr, pad;
     double latent_heat;      // L_v (water) or L_s (ice)
+    signed char s_fice, s_psur, s_tsur, s_qatm, s_tatm, s_patm, s_uatm, s_vatm, s_aev, s_ase, s_qsur_in, s_fare;
+    signed char spad[4];
 };
 
 struct FusedUVType {    // one surface type on the u or v grid
     const double *fice, *psur, *tsur, *a_mom, *uatm, *vatm, *qsur_in, *fare;
     double *qsur, *mom;      // mom = UMOM on the u grid, VMOM on the v grid
     int m_qsur, m_mom;
+    signed char s_fice, s_psur, s_tsur, s_amom, s_uatm, s_vatm, s_qsur_in, s_fare;
+};
+
+constexpr int kMaxStaged = 14;      // input arrays staged per tile; more -> the direct-load kernel is used
+struct StageList {
+    int n;                          // 0: this grid / plan is not staged
+    int pad;
+    const double *src[kMaxStaged];
 };
 
 struct FusedT {
@@ -94,6 +106,7 @@ struct FusedT {
     const double *area;      // cell areas (diagnostics) or null
     // type-0 area-fraction averages (null = not averaged)
     double *avg_qsur, *avg_meva, *avg_hlat, *avg_hsen, *avg_rbbr, *avg_rsdr;
+    signed char s_rsdd, s_bias, s_area, spad[5];
     FusedTType ty[kMaxSurfaceTypes];
 };
 
@@ -103,6 +116,7 @@ struct FusedUV {
     int pad;
     const double *area;
     double *avg_qsur, *avg_mom;
+    signed char s_area, spad[7];
     FusedUVType ty[kMaxSurfaceTypes];
 };
 
@@ -121,6 +135,9 @@ struct FusedPlan {
     int diag_n;              // number of active diagnostics slots
     int prefetch_distance;   // L2 prefetch look-ahead in blocks (0 = off)
     signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index, -1 = inactive
+    int staged;              // 1: stage[] is valid and the staged (bulk copy + mbarrier) kernel may be used
+    int pad2;
+    StageList stage[3];      // per grid: the distinct input arrays of one tile
 };
 
 // diagnostics slot layout: slot(type 0..10, quantity)
@@ -141,6 +158,7 @@ int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
 int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, cudaStream_t stream, int *launches);
 int64_t fused_diag_rows(const FusedPlan &plan);
 int diag_tmp_doubles(int64_t rows, int nslots);
+unsigned long long read_exact_calls();
 int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,
                       double *dst, int64_t n_dst, cudaStream_t stream);

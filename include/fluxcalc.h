@@ -261,12 +261,14 @@ int fc_kernel_time_ms(fc_context *ctx, double *total_ms, int64_t *count);
 /* options: "force_generic" (0/1: use the op-list interpreter kernels instead of the fused kernel),
  *          "pin_host" (0/1: cudaHostRegister bound host arrays), "h2d_chunks" (pipeline depth of the
  *          host-pointer path), "diagnostics" (0 off, 1 area-weighted sums, 2 sums + min/max),
- *          "profile_kernel" (0/1) */
+ *          "profile_kernel" (0/1), "staged" (0/1: allow the shared-memory staged kernel, default 1),
+ *          "prefetch_distance" (L2 prefetch look-ahead of the direct kernel in 512-cell blocks, default 0) */
 int fc_set_option(fc_context *ctx, const char *name, int64_t value);
 int64_t fc_get_info(const fc_context *ctx, const char *name);
 /* info names: "launches" (kernel launches issued so far), "fused" (1 if the fused kernel serves
  * fc_step_*), "bytes_per_cell" (algorithmic bytes of fc_step_all per t/u/v cell triple),
- * "h2d_bytes_per_step", "d2h_bytes_per_step" */
+ * "h2d_bytes_per_step", "d2h_bytes_per_step", "exact_path_calls" (threads of the fused kernel that left the
+ * lock-step fast path and recomputed their cells with the IEEE routines; 0 for physical data) */
 
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics (new, additive; reproduce the reference's debug "range =" lines, flux_calculator.F90:881,

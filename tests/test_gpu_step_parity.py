@@ -8,7 +8,7 @@ from tolerances import check_field
 pytestmark = pytest.mark.gpu
 
 
-def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chunks=None, diagnostics=0):
+def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chunks=None, diagnostics=0, staged=None):
     from components.flux_calculator_b200 import DeviceArray
     # oracle
     o_in, o_out = sc.clone()
@@ -26,6 +26,8 @@ def run_both(fcmod, sc, mode="host", t=0, force_generic=False, phases="all", chu
         fc.set_option("force_generic", 1)
     if chunks:
         fc.set_option("h2d_chunks", chunks)
+    if staged is not None:      # 0: direct-load kernel only, 2: staged (cp.async.bulk + mbarrier) kernel whenever possible
+        fc.set_option("staged", staged)
     if mode == "host":
         sc.apply(fc, g_in, g_out)
         wrapped = None
@@ -59,10 +61,11 @@ def compare(sc, o_out, g_out):
 
 @pytest.mark.parametrize("fset", ["CCLM", "MOM5", "RCO"])
 @pytest.mark.parametrize("mode", ["host", "device"])
-def test_step_all_s1(fcmod, fset, mode):
+@pytest.mark.parametrize("staged", [0, 2])
+def test_step_all_s1(fcmod, fset, mode, staged):
     from components.flux_calculator_b200.synthetic import Scenario
     sc = Scenario(fset, n=(20000, 20000, 20000), S=1, bias=(fset == "MOM5"))
-    fc, o_out, g_out, o_in, g_in = run_both(fcmod, sc, mode)
+    fc, o_out, g_out, o_in, g_in = run_both(fcmod, sc, mode, staged=staged)
     assert fc.info("fused") == 1
     compare(sc, o_out, g_out)
     for k in o_in:      # inputs untouched
@@ -110,13 +113,46 @@ def test_split_phases_equal_fused_all(fcmod):
         assert np.array_equal(a_out[k], s_out[k], equal_nan=True), k
 
 
-@pytest.mark.parametrize("n", [(0, 0, 0), (1, 1, 1), (3, 2, 1), (511, 513, 1025), (33, 0, 7)])
-def test_ragged_and_tiny_grids(fcmod, n):
+@pytest.mark.parametrize("n", [(0, 0, 0), (1, 1, 1), (3, 2, 1), (511, 513, 1025), (33, 0, 7), (5121, 1024, 2047)])
+@pytest.mark.parametrize("staged", [0, 2])
+def test_ragged_and_tiny_grids(fcmod, n, staged):
     from components.flux_calculator_b200.synthetic import Scenario
     sc = Scenario("CCLM", n=n, S=1, bias=True)
     for mode in ("host", "device"):
-        _, o_out, g_out, _, _ = run_both(fcmod, sc, mode)
+        _, o_out, g_out, _, _ = run_both(fcmod, sc, mode, staged=staged)
         compare(sc, o_out, g_out)
+
+
+def test_staged_and_direct_kernels_agree_bitwise(fcmod):
+    """same formula templates, same arithmetic policy: the shared-memory staged kernel and the direct-load kernel
+    must produce identical bits (incl. a persistent grid that wraps: 700 tiles > 2 x 148 CTAs)"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    for fset in ("CCLM", "RCO"):
+        sc = Scenario(fset, n=(358400, 358400 + 77, 358400 - 513), S=1, bias=True)
+        _, o_out, d_out, _, _ = run_both(fcmod, sc, "device", staged=0)
+        _, _, s_out, _, _ = run_both(fcmod, sc, "device", staged=2)
+        compare(sc, o_out, d_out)
+        for k in d_out:
+            assert np.array_equal(d_out[k], s_out[k], equal_nan=True), k
+
+
+def test_extreme_operands_take_the_exact_path(fcmod):
+    """operands outside [2^-500, 2^500] (or -0 / Inf where it matters) leave the lock-step fast path: the thread
+    recomputes its cells with the IEEE routines, results stay bit-exact where no transcendental is involved"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("RCO", n=(4096, 4096, 4096), S=1)
+    before = None
+    for staged in (0, 2):
+        sc.inputs[(0, 2, "UATM")][5] = 1e200      # u*u overflows -> sqrt(inf)
+        sc.inputs[(0, 2, "UATM")][6] = 1e-200     # u*u underflows to a tiny sqrt argument
+        sc.inputs[(0, 3, "VATM")][9] = -0.0
+        fc, o_out, g_out, _, _ = run_both(fcmod, sc, "device", staged=staged)
+        calls = fc.info("exact_path_calls")
+        assert calls > (before or 0)
+        before = calls
+        for k in ((1, 2, "UMOM"), (1, 3, "VMOM")):
+            a, b = g_out[k], o_out[k]
+            assert np.array_equal(a, b, equal_nan=True), k
 
 
 def test_month_rollover_bias(fcmod):
@@ -143,12 +179,13 @@ def test_chunked_host_pipeline(fcmod):
 
 
 @pytest.mark.parametrize("level", [1, 2])
+@pytest.mark.parametrize("staged", [0, 2])
 @pytest.mark.parametrize("S,n", [(2, (10007, 10009, 10011)), (1, (200000, 150001, 99999)), (1, (3, 700, 0))])
-def test_diagnostics(fcmod, level, S, n):
+def test_diagnostics(fcmod, level, S, n, staged):
     from components.flux_calculator_b200.synthetic import Scenario
     sc = Scenario("CCLM", n=n, S=S, bias=True, averaging=True)
     for mode in ("device", "host"):
-        fc, o_out, g_out, _, _ = run_both(fcmod, sc, mode, diagnostics=level)
+        fc, o_out, g_out, _, _ = run_both(fcmod, sc, mode, diagnostics=level, staged=staged)
         compare(sc, o_out, g_out)
         for (i, g, name), arr in g_out.items():
             if arr.size == 0:
