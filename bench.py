@@ -310,7 +310,8 @@ def main():
     diag_sample = None
     if diag:
         s_, mn_, mx_ = fc.diagnostics(1, 1, "HSEN")
-        diag_sample = {"HSEN_type1": {"sum_area_x": s_, "min": mn_, "max": mx_}}
+        nn = lambda v: None if v != v else v      # NaN (min/max are only computed at diagnostics level 2) -> null
+        diag_sample = {"HSEN_type1": {"sum_area_x": s_, "min": nn(mn_), "max": nn(mx_)}}
 
     # ---------------- end-to-end through the C ABI with host arrays ----------------
     e2e = None

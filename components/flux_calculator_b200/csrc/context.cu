@@ -281,7 +281,12 @@ extern "C" int fc_destroy(fc_context *c)
     for (int g = 1; g <= 3; ++g)
         if (c->area_owned[g]) cudaFree(c->area_dev[g]);
     cudaFree(c->diag_partials);
-    cudaFree(c->diag_dev);
+    for (int b = 0; b < 2; ++b) {
+        cudaFree(c->diag_buf[b]);
+        if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]);
+        if (c->ev_comm[b]) cudaEventDestroy(c->ev_comm[b]);
+    }
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->diag_host) cudaFreeHost(c->diag_host);
     for (auto &m : c->regrid) free_regrid(m);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
@@ -480,6 +485,7 @@ extern "C" int fc_synchronize(fc_context *c)
     if (!c) return fail(nullptr, FC_ERR_ARG, "NULL context");
     cudaSetDevice(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->comm_stream) CUDA_TRY(c, cudaStreamSynchronize(c->comm_stream));
     return FC_OK;
 }
 
@@ -1309,7 +1315,12 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P)
         CUDA_TRY(c, cudaMalloc(&c->diag_partials, need));
         c->diag_partials_cap = need;
     }
-    if (!c->diag_dev) CUDA_TRY(c, cudaMalloc(&c->diag_dev, sizeof(double) * kDiagSlots * 3));
+    for (int b = 0; b < 2; ++b)
+        if (!c->diag_buf[b]) {
+            CUDA_TRY(c, cudaMalloc(&c->diag_buf[b], sizeof(double) * kDiagSlots * 3));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_fin[b], cudaEventDisableTiming));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_comm[b], cudaEventDisableTiming));
+        }
     if (!c->diag_host) CUDA_TRY(c, cudaHostAlloc(&c->diag_host, sizeof(double) * kDiagSlots * 3 * 2, cudaHostAllocDefault));
     P.diag_partials = c->diag_partials;
     P.diag_rows = rows;
@@ -1320,6 +1331,24 @@ static double *diag_tmp(fc_context *c, const FusedPlan &P)
 {
     const int planes = P.diag >= 2 ? 3 : 1;
     return c->diag_partials + (size_t)planes * P.diag_n * (size_t)P.diag_rows;
+}
+
+// partial rows -> diag_buf[next]; if that buffer's previous all-reduce is still in flight on the side stream, wait
+static int finalize_diag(fc_context *c, const FusedPlan &P, const FusedBundle &F)
+{
+    const int b = c->diag_cur ^ 1;
+    if (c->comm_busy[b]) {
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_comm[b], 0));
+        c->comm_busy[b] = false;
+    }
+    int nl = 0;
+    if (launch_diag_finalize(P, diag_tmp(c, P), c->diag_buf[b], c->stream, &nl)) return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
+    c->launches += nl;
+    c->diag_cur = b;
+    c->diag_active = F.diag_slots;
+    c->diag_valid = false;
+    c->diag_level = P.diag;
+    return FC_OK;
 }
 
 static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
@@ -1357,13 +1386,7 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         if (e1) CUDA_TRY(c, cudaEventRecord(e1, c->stream));
         c->launches += nlaunch;
         if (P.diag) {
-            int nl = 0;
-            if (launch_diag_finalize(P, diag_tmp(c, P), c->diag_dev, c->stream, &nl))
-                return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
-            c->launches += nl;
-            c->diag_active = F.diag_slots;
-            c->diag_valid = false;
-            c->diag_level = P.diag;
+            if (int rc = finalize_diag(c, P, F)) return rc;
         }
         if (!F.extra.empty())
             if (int rc = run_ops(c, F.extra)) return rc;
@@ -1411,13 +1434,7 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     c->launches += nlaunch;
     for (int k = 0; k < 3; ++k) CUDA_TRY(c, cudaStreamSynchronize(c->pipe[k]));
     if (P.diag) {
-        int nl = 0;
-        if (launch_diag_finalize(P, diag_tmp(c, P), c->diag_dev, c->stream, &nl))
-            return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
-        c->launches += nl;
-        c->diag_active = F.diag_slots;
-        c->diag_valid = false;
-        c->diag_level = P.diag;
+        if (int rc = finalize_diag(c, P, F)) return rc;
     }
     if (!F.extra.empty())
         if (int rc = run_ops(c, F.extra)) return rc;
@@ -1463,6 +1480,11 @@ extern "C" int fc_event_record(fc_context *c, int which)
     if (!c || which < 0 || which > 1) return fail(c, FC_ERR_ARG, "fc_event_record: bad argument");
     cudaSetDevice(c->device);
     if (!c->user_ev[which]) CUDA_TRY(c, cudaEventCreate(&c->user_ev[which]));
+    for (int b = 0; b < 2; ++b)      // an event on the main stream also covers all-reduces still running on the side stream
+        if (c->comm_busy[b]) {
+            CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_comm[b], 0));
+            c->comm_busy[b] = false;
+        }
     CUDA_TRY(c, cudaEventRecord(c->user_ev[which], c->stream));
     return FC_OK;
 }
@@ -1552,11 +1574,16 @@ int diag_fetch(fc_context *c)
     if (c->diag_valid) return FC_OK;
     if (c->diag_active.empty()) return fail(c, FC_ERR_STATE, "no diagnostics available: enable option 'diagnostics' and run a step");
     cudaSetDevice(c->device);
-    double *compact = c->diag_host + kDiagSlots * 3;
-    CUDA_TRY(c, cudaMemcpyAsync(compact, c->diag_dev, sizeof(double) * c->diag_active.size() * 3, cudaMemcpyDeviceToHost, c->stream));
+    const int b = c->diag_cur;
+    if (c->comm_busy[b]) {      // the all-reduce of this buffer runs on the side stream
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_comm[b], 0));
+        c->comm_busy[b] = false;
+    }
+    double *planes = c->diag_host + kDiagSlots * 3;
+    CUDA_TRY(c, cudaMemcpyAsync(planes, c->diag_buf[b], sizeof(double) * kDiagSlots * 3, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (size_t k = 0; k < c->diag_active.size(); ++k)
-        for (int j = 0; j < 3; ++j) c->diag_host[c->diag_active[k] * 3 + j] = compact[k * 3 + j];
+        for (int j = 0; j < 3; ++j) c->diag_host[c->diag_active[k] * 3 + j] = planes[j * kDiagSlots + k];
     c->diag_valid = true;
     return FC_OK;
 }

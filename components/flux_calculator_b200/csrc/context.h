@@ -116,7 +116,11 @@ struct fc_context {
     // diagnostics storage
     double *diag_partials = nullptr;
     size_t diag_partials_cap = 0;
-    double *diag_dev = nullptr;          // [kDiagSlots][3] compact
+    double *diag_buf[2] = {nullptr, nullptr};   // [sum|min|max][kDiagSlots] compact slots, double buffered by step
+    int diag_cur = 0;                    // buffer the last step wrote
+    cudaStream_t comm_stream = nullptr;  // NCCL all-reduce runs here, overlapped with the next step
+    cudaEvent_t ev_fin[2] = {nullptr, nullptr}, ev_comm[2] = {nullptr, nullptr};
+    bool comm_busy[2] = {false, false};
     double *diag_host = nullptr;         // pinned copy, expanded to [kDiagSlots][3]
     std::vector<int> diag_active;        // slot ids in compact order (of the last step)
     bool diag_valid = false;

@@ -869,10 +869,10 @@ diag_reduce_final_kernel(const double *__restrict__ tmp, int nchunks, int planes
         }
     }
     block_combine(s, mn, mx, planes);
-    if (threadIdx.x == 0) {
-        out[slot * 3 + 0] = s;
-        out[slot * 3 + 1] = mn;
-        out[slot * 3 + 2] = mx;
+    if (threadIdx.x == 0) {      // plane-major [sum | min | max][kDiagSlots]: each plane is one NCCL all-reduce
+        out[0 * kDiagSlots + slot] = s;
+        out[1 * kDiagSlots + slot] = mn;
+        out[2 * kDiagSlots + slot] = mx;
     }
 }
 

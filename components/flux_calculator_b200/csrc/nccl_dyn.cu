@@ -3,7 +3,7 @@
 // libnccl.so.2 is dlopen'ed on first use: a Fortran host gets the system NCCL, a Python process that
 // already imported torch gets torch's bundled copy (same SONAME -> same handle), and a single-GPU run
 // never needs NCCL at all.  Per step the traffic is < 3 KB (sum / min / max vectors), so on NVSwitch
-// only the ~10-20 us latency matters; it runs on the context's stream behind the finalize kernel.
+// only the ~10-20 us latency matters; it runs on a side stream, overlapped with the next step's kernel.
 #include "context.h"
 
 #include <dlfcn.h>
@@ -47,20 +47,6 @@ NcclApi &api()
     return a;
 }
 
-// gather (sum | min | max) columns of the compact [n][3] diagnostics into three contiguous vectors and back
-__global__ void diag_split_kernel(const double *__restrict__ d, double *__restrict__ cols, int n)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n)
-        for (int j = 0; j < 3; ++j) cols[j * n + k] = d[k * 3 + j];
-}
-__global__ void diag_merge_kernel(double *__restrict__ d, const double *__restrict__ cols, int n)
-{
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n)
-        for (int j = 0; j < 3; ++j) d[k * 3 + j] = cols[j * n + k];
-}
-
 }  // namespace
 
 namespace fc {
@@ -71,31 +57,36 @@ void nccl_destroy(fc_context *c)
     c->nccl_comm = nullptr;
 }
 
+// The diagnostics of the step just issued live plane-major ([sum|min|max][kDiagSlots]) in diag_buf[cur]; each
+// plane is reduced in place by one ncclAllReduce on a SIDE stream, so the main stream goes straight on to the
+// next step's kernel.  The buffer is reused two steps later (finalize_diag waits for ev_comm then).
 int nccl_allreduce_diag(fc_context *c)
 {
     NcclApi &a = api();
     if (!a.ok) return fail(c, FC_ERR_NCCL, "libnccl.so.2 could not be loaded");
     cudaSetDevice(c->device);
     const int n = (int)c->diag_active.size();
-    static_assert(sizeof(double) * kDiagSlots * 3 >= 1, "");
-    // scratch: reuse the tail of diag_dev ([kDiagSlots][3] allocated, n <= kDiagSlots used) needs 3n more doubles
-    double *cols = nullptr;
-    CUDA_TRY(c, cudaMallocAsync(&cols, sizeof(double) * 3 * n, c->stream));
-    diag_split_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->diag_dev, cols, n);
+    const int b = c->diag_cur;
+    if (!c->comm_stream) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaEventRecord(c->ev_fin[b], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->comm_stream, c->ev_fin[b], 0));
+    double *buf = c->diag_buf[b];
     ncclComm_t comm = (ncclComm_t)c->nccl_comm;
-    ncclResult_t r = a.GroupStart();
-    if (r == ncclSuccess) r = a.AllReduce(cols, cols, n, ncclDouble, ncclSum, comm, c->stream);
-    if (r == ncclSuccess) r = a.AllReduce(cols + n, cols + n, n, ncclDouble, ncclMin, comm, c->stream);
-    if (r == ncclSuccess) r = a.AllReduce(cols + 2 * n, cols + 2 * n, n, ncclDouble, ncclMax, comm, c->stream);
-    ncclResult_t r2 = a.GroupEnd();
-    if (r == ncclSuccess) r = r2;
-    if (r != ncclSuccess) {
-        cudaFreeAsync(cols, c->stream);
-        return fail(c, FC_ERR_NCCL, "ncclAllReduce failed: %s", a.GetErrorString(r));
+    ncclResult_t r = ncclSuccess;
+    if (c->diag_level >= 2) {
+        r = a.GroupStart();
+        if (r == ncclSuccess) r = a.AllReduce(buf, buf, n, ncclDouble, ncclSum, comm, c->comm_stream);
+        if (r == ncclSuccess) r = a.AllReduce(buf + kDiagSlots, buf + kDiagSlots, n, ncclDouble, ncclMin, comm, c->comm_stream);
+        if (r == ncclSuccess) r = a.AllReduce(buf + 2 * kDiagSlots, buf + 2 * kDiagSlots, n, ncclDouble, ncclMax, comm, c->comm_stream);
+        const ncclResult_t r2 = a.GroupEnd();
+        if (r == ncclSuccess) r = r2;
+    } else {
+        r = a.AllReduce(buf, buf, n, ncclDouble, ncclSum, comm, c->comm_stream);
     }
-    diag_merge_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->diag_dev, cols, n);
-    CUDA_TRY(c, cudaFreeAsync(cols, c->stream));
-    c->launches += 2;
+    if (r != ncclSuccess) return fail(c, FC_ERR_NCCL, "ncclAllReduce failed: %s", a.GetErrorString(r));
+    CUDA_TRY(c, cudaEventRecord(c->ev_comm[b], c->comm_stream));
+    c->comm_busy[b] = true;
+    c->launches += 1;
     return FC_OK;
 }
 
