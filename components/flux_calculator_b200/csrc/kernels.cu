@@ -1,15 +1,15 @@
 // kernels.cu -- hand-written sm_100a kernels of the flux calculator hot path.
 //
-//  fused_step_kernel   one launch per coupling-step phase: t-, u- and v-grid chains of every surface
-//                      type in one pass over SoA fields, all intermediates (QSUR, MEVA, vel, T~,
-//                      flux_air) in registers, 128-bit coalesced loads/stores, optional diagnostics
-//                      epilogue (warp shuffle -> shared -> per-block partials).
+//  fused_step_kernel   generic fused pass (any number of surface types, any method mix, averaging): t-, u-
+//                      and v-grid chains of every surface type in one pass over SoA fields, intermediates in
+//                      registers, 128-bit coalesced loads/stores, per-warp diagnostics partials.  Also the
+//                      guarded variant for ragged remainders / misaligned arrays.  The specialised persistent
+//                      kernel of spec_kernel.cu takes over for the canonical single-surface-type plans.
 //  oplist_kernel       interpreter for the reference's pass sequence (exact semantics for aliased
 //                      outputs / unfused calc_* calls / the Level-1 flux_lib array routines).
 //  diag_finalize, transpose_corrections, regrid_csr: small helpers.
 //
-// The path is elementwise FP64 streaming: HBM-bound, no reuse across cells, so no tensor cores, no
-// shared-memory staging (ncu: see profiles/).
+// The path is elementwise FP64 streaming: HBM-bound, no reuse across cells, so no tensor cores.
 #include "plan.h"
 
 #include <cuda_runtime.h>
@@ -30,10 +30,8 @@ using Exact = ExactVec<V>;
 // Loader policies: where a thread's V cells of an input array come from, and how results are stored.
 //   LdGlobal : 128-bit global loads/stores (every array 16-byte aligned, all V cells valid)
 //   LdGuard  : guarded scalar accesses (ragged tail of a grid, misaligned arrays)
-//   LdStaged : inputs from the shared-memory stage a bulk copy (cp.async.bulk) filled, 128-bit global stores
 struct LdGlobal {
     static constexpr bool kFull = true;
-    static constexpr bool kLazy = false;
     int64_t j;
     __device__ __forceinline__ V2 load(const double *__restrict__ p, int) const
     {
@@ -48,12 +46,10 @@ struct LdGlobal {
     {
         *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
     }
-    __device__ __forceinline__ void release() const {}
 };
 
 struct LdGuard {
     static constexpr bool kFull = false;
-    static constexpr bool kLazy = false;
     int64_t j;
     int nv;
     __device__ __forceinline__ V2 load(const double *__restrict__ p, int) const
@@ -68,46 +64,6 @@ struct LdGuard {
 #pragma unroll
         for (int k = 0; k < V; ++k)
             if (k < nv) p[j + k] = x.v[k];
-    }
-    __device__ __forceinline__ void release() const {}
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar);
-
-constexpr int kStageSlotBytes = kFusedCellsPerBlock * 8;      // one array of one tile
-struct LdStaged {
-    static constexpr bool kFull = true;
-    static constexpr bool kLazy = true;
-    int64_t j;
-    const char *stage;      // this thread's 16 bytes of slot 0
-    uint64_t *empty;        // "stage may be refilled" barrier
-    // called by the chain right after its last read of the stage: the inputs now live in registers, so the
-    // producer can refill this stage while the arithmetic runs (keeps >= 1 tile per CTA in flight at all times)
-    __device__ __forceinline__ void release() const
-    {
-#ifdef FC_EARLY_RELEASE
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
-#endif
-    }
-    __device__ __forceinline__ void release_at_end() const
-    {
-#ifndef FC_EARLY_RELEASE
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) mbar_arrive(empty);
-#endif
-    }
-    __device__ __forceinline__ V2 load(const double *, int slot) const
-    {
-        const double2 t = *reinterpret_cast<const double2 *>(stage + slot * kStageSlotBytes);
-        V2 r;
-        r.v[0] = t.x;
-        r.v[1] = t.y;
-        return r;
-    }
-    __device__ __forceinline__ void store(double *p, const V2 &x) const
-    {
-        *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
     }
 };
 
@@ -153,21 +109,11 @@ struct DiagCtx {
     int64_t rows;        // row stride (total warp rows of the launch)
     int64_t row;         // this warp's row
     int64_t plane;       // slots * rows
-    double acc[DQ_COUNT];   // DIAG == 3: this thread's running sums (persistent staged kernel, S == 1)
 };
 
-// DIAG == 3 (staged kernel, sums only, one surface type): the thread just accumulates; the warp tree and the store
-// happen once per kernel instead of once per tile
 template <int DIAG>
 __device__ __forceinline__ void diag_commit(const FusedPlan &p, DiagCtx &d, int base, int q, const V2 &x, const V2 &area, int nv)
 {
-    if (DIAG == 3) {
-        double s = 0.0;
-#pragma unroll
-        for (int k = 0; k < V; ++k) s = add(s, mul(area.v[k], x.v[k]));
-        d.acc[q] = add(d.acc[q], s);
-        return;
-    }
     const int slot = base + q;
     double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
 #pragma unroll
@@ -201,7 +147,7 @@ __device__ __forceinline__ void diag_commit(const FusedPlan &p, DiagCtx &d, int 
 // ---------------------------------------------------------------------------------------------
 // per-surface-type arithmetic of the t grid, instantiated with the fast and the exact policy
 // ---------------------------------------------------------------------------------------------
-// inputs of one surface type: preloaded into registers (direct-load kernels) ...
+// inputs of one surface type, preloaded into registers
 struct TIn {
     V2 fice_, psur_, tsur_, qatm_, tatm_, patm_, uatm_, vatm_, aev_, ase_, qsur_in_, bias_;
     __device__ __forceinline__ const V2 &fice() const { return fice_; }
@@ -216,43 +162,6 @@ struct TIn {
     __device__ __forceinline__ const V2 &ase() const { return ase_; }
     __device__ __forceinline__ const V2 &qsur_in() const { return qsur_in_; }
     __device__ __forceinline__ const V2 &bias() const { return bias_; }
-};
-// ... or read from the shared-memory stage at the point of use (staged kernel): nothing is held in registers
-// longer than the expression that needs it, a re-read costs one LDS.128
-template <class LD>
-struct TInLazy {
-    const LD &ld;
-    const FusedTType &ty;
-    const FusedT &t;
-    __device__ __forceinline__ V2 fice() const { return ld.load(ty.fice, ty.s_fice); }
-    __device__ __forceinline__ V2 psur() const { return ld.load(ty.psur, ty.s_psur); }
-    __device__ __forceinline__ V2 tsur() const { return ld.load(ty.tsur, ty.s_tsur); }
-    __device__ __forceinline__ V2 qatm() const { return ld.load(ty.qatm, ty.s_qatm); }
-    __device__ __forceinline__ V2 tatm() const { return ld.load(ty.tatm, ty.s_tatm); }
-    __device__ __forceinline__ V2 patm() const { return ld.load(ty.patm, ty.s_patm); }
-    __device__ __forceinline__ V2 uatm() const { return ld.load(ty.uatm, ty.s_uatm); }
-    __device__ __forceinline__ V2 vatm() const { return ld.load(ty.vatm, ty.s_vatm); }
-    __device__ __forceinline__ V2 aev() const { return ld.load(ty.a_evap, ty.s_aev); }
-    __device__ __forceinline__ V2 ase() const { return ld.load(ty.a_sens, ty.s_ase); }
-    __device__ __forceinline__ V2 qsur_in() const { return ld.load(ty.qsur_in, ty.s_qsur_in); }
-    __device__ __forceinline__ V2 bias() const { return ld.load(t.bias, t.s_bias); }
-    __device__ __forceinline__ TIn materialize() const     // cold path only: unstaged (null) fields stay unset
-    {
-        TIn in;
-        if (ty.s_fice >= 0) in.fice_ = fice();
-        if (ty.s_psur >= 0) in.psur_ = psur();
-        if (ty.s_tsur >= 0) in.tsur_ = tsur();
-        if (ty.s_qatm >= 0) in.qatm_ = qatm();
-        if (ty.s_tatm >= 0) in.tatm_ = tatm();
-        if (ty.s_patm >= 0) in.patm_ = patm();
-        if (ty.s_uatm >= 0) in.uatm_ = uatm();
-        if (ty.s_vatm >= 0) in.vatm_ = vatm();
-        if (ty.s_aev >= 0) in.aev_ = aev();
-        if (ty.s_ase >= 0) in.ase_ = ase();
-        if (ty.s_qsur_in >= 0) in.qsur_in_ = qsur_in();
-        if (t.s_bias >= 0) in.bias_ = bias();
-        return in;
-    }
 };
 struct TOut {
     V2 qsur, meva, hlat, hsen, rbbr;
@@ -305,7 +214,7 @@ unsigned long long read_exact_calls()
 {
     unsigned long long v = 0;
     cudaMemcpyFromSymbol(&v, g_exact_calls, sizeof v);
-    return v;
+    return v + read_spec_exact_calls();
 }
 
 // recompute path (an operand left the range in which the lock-step sequences are proven): out of line, cold
@@ -329,7 +238,7 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv
     V2 rsdd, area;
     const bool has_bias = p.do_normal && t.bias != nullptr;
     const bool has_rsdr = p.do_normal && t.rsdd != nullptr;
-    if (has_bias && !LD::kLazy) in.bias_ = ld.load(t.bias, t.s_bias);
+    if (has_bias) in.bias_ = ld.load(t.bias, t.s_bias);
     if (has_rsdr) rsdd = ld.load(t.rsdd, t.s_rsdd);
     if (DIAG) area = ld.load(t.area, t.s_area);
     V2 aQ = vzero(), aM = vzero(), aL = vzero(), aH = vzero(), aR = vzero(), aS = vzero();   // type-0 averages
@@ -341,26 +250,21 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv
         if (LD::kFull || nv) {
             // all loads of this surface type up front (memory-level parallelism), then arithmetic
             if (ty.fare) fare = ld.load(ty.fare, ty.s_fare);
-            if constexpr (LD::kLazy) {
-                const TInLazy<LD> lin{ld, ty, t};
-                if (t_type_math<Fast>(p, ty, lin, has_bias, o)) o = t_type_exact(p, i, lin.materialize(), has_bias);
-            } else {
-                in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
-                if (p.do_normal) {
-                    in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
-                    in.qatm_ = cQATM.get(ld, ty.qatm, ty.s_qatm);
-                    in.tatm_ = cTATM.get(ld, ty.tatm, ty.s_tatm);
-                    in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
-                    in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
-                    in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
-                    in.aev_ = cAEV.get(ld, ty.a_evap, ty.s_aev);
-                    in.ase_ = cASE.get(ld, ty.a_sens, ty.s_ase);
-                    in.patm_ = cPATM.get(ld, ty.patm, ty.s_patm);
-                    if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
-                }
-                if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
-                    o = t_type_exact(p, i, in, has_bias);             // redo these cells with the IEEE routines
+            in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
+            if (p.do_normal) {
+                in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
+                in.qatm_ = cQATM.get(ld, ty.qatm, ty.s_qatm);
+                in.tatm_ = cTATM.get(ld, ty.tatm, ty.s_tatm);
+                in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
+                in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
+                in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
+                in.aev_ = cAEV.get(ld, ty.a_evap, ty.s_aev);
+                in.ase_ = cASE.get(ld, ty.a_sens, ty.s_ase);
+                in.patm_ = cPATM.get(ld, ty.patm, ty.s_patm);
+                if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
             }
+            if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
+                o = t_type_exact(p, i, in, has_bias);             // redo these cells with the IEEE routines
             if (p.do_normal) {
                 if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
                 if (ty.m_meva != M_NONE) ld.store(ty.meva, o.meva);
@@ -426,30 +330,6 @@ struct UVIn {
     __device__ __forceinline__ const V2 &vatm() const { return vatm_; }
     __device__ __forceinline__ const V2 &qsur_in() const { return qsur_in_; }
 };
-template <class LD>
-struct UVInLazy {
-    const LD &ld;
-    const FusedUVType &ty;
-    __device__ __forceinline__ V2 fice() const { return ld.load(ty.fice, ty.s_fice); }
-    __device__ __forceinline__ V2 psur() const { return ld.load(ty.psur, ty.s_psur); }
-    __device__ __forceinline__ V2 tsur() const { return ld.load(ty.tsur, ty.s_tsur); }
-    __device__ __forceinline__ V2 amom() const { return ld.load(ty.a_mom, ty.s_amom); }
-    __device__ __forceinline__ V2 uatm() const { return ld.load(ty.uatm, ty.s_uatm); }
-    __device__ __forceinline__ V2 vatm() const { return ld.load(ty.vatm, ty.s_vatm); }
-    __device__ __forceinline__ V2 qsur_in() const { return ld.load(ty.qsur_in, ty.s_qsur_in); }
-    __device__ __forceinline__ UVIn materialize() const
-    {
-        UVIn in;
-        if (ty.s_fice >= 0) in.fice_ = fice();
-        if (ty.s_psur >= 0) in.psur_ = psur();
-        if (ty.s_tsur >= 0) in.tsur_ = tsur();
-        if (ty.s_amom >= 0) in.amom_ = amom();
-        if (ty.s_uatm >= 0) in.uatm_ = uatm();
-        if (ty.s_vatm >= 0) in.vatm_ = vatm();
-        if (ty.s_qsur_in >= 0) in.qsur_in_ = qsur_in();
-        return in;
-    }
-};
 struct UVOut {
     V2 qsur, mom;
 };
@@ -501,19 +381,14 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
         UVOut o;
         if (LD::kFull || nv) {
             if (ty.fare) fare = ld.load(ty.fare, ty.s_fare);
-            if constexpr (LD::kLazy) {
-                const UVInLazy<LD> lin{ld, ty};
-                if (uv_type_math<Fast>(p, ty, lin, g.north, o)) o = uv_type_exact(p, which, i, lin.materialize());
-            } else {
-                in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
-                in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
-                in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
-                in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
-                in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
-                in.amom_ = cAMOM.get(ld, ty.a_mom, ty.s_amom);
-                if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
-                if (uv_type_math<Fast>(p, ty, in, g.north, o)) o = uv_type_exact(p, which, i, in);
-            }
+            in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
+            in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
+            in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
+            in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
+            in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
+            in.amom_ = cAMOM.get(ld, ty.a_mom, ty.s_amom);
+            if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
+            if (uv_type_math<Fast>(p, ty, in, g.north, o)) o = uv_type_exact(p, which, i, in);
             if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
             if (ty.m_mom != M_NONE) ld.store(ty.mom, o.mom);
             if (g.avg_qsur) avg_acc(aQ, o.qsur, fare);
@@ -651,140 +526,6 @@ fused_step_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ L
         const LdGuard ld{j, nv};
         if (which == 0) t_chain<SS, DIAG>(p, ld, nv, dg);
         else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, nv, dg);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// staged variant: persistent CTAs, one producer warp streams the input arrays of 512-cell tiles into a ring of
-// shared-memory stages with cp.async.bulk (completion counted on an mbarrier), eight consumer warps run the
-// same chains reading their cells from shared memory.  The bytes in flight per SM are then set by the ring
-// (>= 48 KB per CTA), not by registers x resident warps -- ncu showed long_scoreboard as the dominant stall of
-// the direct-load kernel at 16 resident warps/SM, worst on the light u/v chains (2-6 loads per thread).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred P_OUT;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 P_OUT, [%1], %2;\n\t"
-                 "selp.b32 %0, 1, 0, P_OUT;\n\t}"
-                 : "=r"(done)
-                 : "r"(smem_u32(bar)), "r"(parity)
-                 : "memory");
-    return done != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-constexpr int kStagedConsumers = kFusedThreads;              // 8 consumer warps = one 512-cell tile
-constexpr int kStagedThreads = kStagedConsumers + 32;        // + 1 producer warp
-constexpr int kMaxStages = 8;
-
-struct StagedGeom {
-    int64_t first[3];        // first cell of the staged range on each grid
-    int ntiles[3];           // whole tiles per grid
-    int nstages;
-    int stage_bytes;
-    int64_t row0;            // first diagnostics row
-};
-
-template <int SS, int DIAG>
-__global__ void __launch_bounds__(kStagedThreads, 2)
-fused_step_staged_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ StagedGeom geo)
-{
-    extern __shared__ __align__(128) char stage_mem[];
-    __shared__ uint64_t full_bar[kMaxStages], empty_bar[kMaxStages];
-    const int NS = geo.nstages;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full_bar[s], 1);                          // one expect_tx arrival + the bytes
-            mbar_init(&empty_bar[s], kStagedConsumers / 32);     // one arrival per consumer warp
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    const int total = geo.ntiles[0] + geo.ntiles[1] + geo.ntiles[2];
-    const int warp = threadIdx.x >> 5;
-    auto decode = [&](int tile, int &which, int64_t &cell) {
-        which = (tile < geo.ntiles[0]) ? 0 : (tile < geo.ntiles[0] + geo.ntiles[1] ? 1 : 2);
-        const int idx = (which == 0) ? tile : (which == 1 ? tile - geo.ntiles[0] : tile - geo.ntiles[0] - geo.ntiles[1]);
-        cell = geo.first[which] + (int64_t)idx * kFusedCellsPerBlock;
-    };
-    if (warp == kStagedConsumers / 32) {
-        // ---------------- producer warp: one lane issues the bulk copies ----------------
-        if ((threadIdx.x & 31) == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-                const int s = it % NS;
-                if (it >= NS) mbar_wait(&empty_bar[s], ((it / NS) - 1) & 1);
-                int which;
-                int64_t cell;
-                decode(tile, which, cell);
-                const StageList &L = p.stage[which];
-                mbar_expect_tx(&full_bar[s], (uint32_t)L.n * kStageSlotBytes);
-                char *dst = stage_mem + (size_t)s * geo.stage_bytes;
-                for (int a = 0; a < L.n; ++a) bulk_g2s(dst + a * kStageSlotBytes, L.src[a] + cell, kStageSlotBytes, &full_bar[s]);
-            }
-        }
-        return;
-    }
-    // ---------------- consumer warps ----------------
-    DiagCtx dg;
-    if (DIAG) {
-        dg.base = p.diag_partials;
-        dg.rows = p.diag_rows;
-        dg.plane = (int64_t)p.diag_n * p.diag_rows;
-#pragma unroll
-        for (int q = 0; q < DQ_COUNT; ++q) dg.acc[q] = 0.0;
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int s = it % NS;
-        int which;
-        int64_t cell;
-        decode(tile, which, cell);
-        mbar_wait(&full_bar[s], (it / NS) & 1);
-        const LdStaged ld{cell + (int64_t)threadIdx.x * V, stage_mem + (size_t)s * geo.stage_bytes + threadIdx.x * (V * 8),
-                          &empty_bar[s]};
-        if (DIAG) dg.row = geo.row0 + (int64_t)tile * (kStagedConsumers / 32) + warp;
-        if (which == 0) t_chain<SS, DIAG>(p, ld, V, dg);
-        else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, V, dg);
-        ld.release_at_end();      // stage s may be refilled
-    }
-    if (DIAG == 3) {
-        // one warp tree + one store per field for the whole kernel; row = this consumer warp
-        const int64_t row = geo.row0 + (int64_t)blockIdx.x * (kStagedConsumers / 32) + warp;
-#pragma unroll
-        for (int q = 0; q < DQ_COUNT; ++q) {
-            const int cs = p.diag_map[DQ_COUNT + q];      // surface type 1
-            if (cs < 0) continue;
-            double v = dg.acc[q];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v = add(v, __shfl_down_sync(0xffffffffu, v, off));
-            if ((threadIdx.x & 31) == 0) p.diag_partials[(int64_t)cs * p.diag_rows + row] = v;
-        }
     }
 }
 
@@ -994,15 +735,16 @@ static bool plan_aligned(const FusedPlan &p)
 }
 
 // geometry of the (up to) two launches of one fused step: whole 512-cell blocks through the 128-bit kernel
-// (staged or direct), the ragged remainder (or everything, if an array is misaligned) through the guarded kernel
+// (specialised persistent kernel or generic direct-load kernel), the ragged remainder (or everything, if an array is
+// misaligned) through the guarded kernel
 struct FusedGeom {
     LaunchGeom main, tail;
     int nb_main, nb_tail;
-    bool staged;
-    bool diag_accum;     // staged kernel accumulates the diagnostics per thread: one row per consumer warp of the grid
-    StagedGeom sg;
-    int staged_grid;
-    size_t staged_smem;
+    bool spec;           // main part runs on the specialised persistent kernel (spec_kernel.cu)
+    bool diag_accum;     // ... which accumulates the diagnostics per thread: one row per consumer warp of its grid
+    int spec_grid;
+    int64_t spec_first[3];
+    int spec_ntiles[3];
 };
 
 static int num_sms()
@@ -1043,33 +785,18 @@ static FusedGeom fused_geometry(const FusedPlan &p)
     G.tail.row0 = (int64_t)G.nb_main * (kFusedThreads / 32);
     G.main.prefetch_distance = p.prefetch_distance;
     G.tail.prefetch_distance = 0;
-    // staged variant: surface-type-static kernels only (S == 1), every active grid staged, >= 2 stages per CTA
-    G.staged = false;
-    if (p.S == 1 && ((p.staged == 1 && G.nb_main >= 4 * num_sms()) || (p.staged == 2 && G.nb_main > 0))) {   // small grids: direct kernel
-        int nmax = 0;
-        bool ok = true;
-        for (int g = 0; g < 3; ++g)
-            if (nbm[g] > 0) {
-                ok = ok && p.stage[g].n > 0;
-                nmax = p.stage[g].n > nmax ? p.stage[g].n : nmax;
-            }
-        const int budget = 110 * 1024;      // two CTAs per SM share 227 KB
-        const int stage_bytes = nmax * kStageSlotBytes;
-        const int ns = (ok && stage_bytes > 0) ? budget / stage_bytes : 0;
-        if (ns >= 2) {
-            G.staged = true;
-            for (int g = 0; g < 3; ++g) {
-                G.sg.first[g] = G.main.first[g];
-                G.sg.ntiles[g] = nbm[g];
-            }
-            G.sg.nstages = ns > kMaxStages ? kMaxStages : ns;
-            G.sg.stage_bytes = stage_bytes;
-            G.sg.row0 = 0;
-            G.staged_smem = (size_t)G.sg.nstages * stage_bytes;
-            const int cap = 2 * num_sms();
-            G.staged_grid = G.nb_main < cap ? G.nb_main : cap;
-            G.diag_accum = (p.diag == 1);
-            if (G.diag_accum) G.tail.row0 = (int64_t)G.staged_grid * (kFusedThreads / 32);
+    // specialised persistent kernel for the canonical single-surface-type plans (small grids: direct kernel)
+    G.spec = false;
+    if (p.S == 1 && ((p.staged == 1 && G.nb_main >= 4 * num_sms()) || (p.staged == 2 && G.nb_main > 0))) {
+        for (int g = 0; g < 3; ++g) {
+            G.spec_first[g] = G.main.first[g];
+            G.spec_ntiles[g] = nbm[g];
+        }
+        G.spec_grid = spec_applicable(p, G.spec_first, G.spec_ntiles);
+        if (G.spec_grid > 0) {
+            G.spec = true;
+            G.diag_accum = (p.diag != 0);
+            if (G.diag_accum) G.tail.row0 = (int64_t)G.spec_grid * (kFusedThreads / 32);
         }
     }
     return G;
@@ -1082,31 +809,11 @@ int64_t fused_diag_rows(const FusedPlan &p)
 }
 
 template <int SS, int DIAG>
-static cudaError_t launch_staged(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream)
-{
-    static size_t configured = 0;
-    if (G.staged_smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_step_staged_kernel<SS, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)G.staged_smem);
-        if (e != cudaSuccess) return e;
-        // two CTAs per SM must fit: ask for the largest shared-memory carveout
-        e = cudaFuncSetAttribute(fused_step_staged_kernel<SS, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-        if (e != cudaSuccess) return e;
-        configured = G.staged_smem;
-    }
-    // persistent grid: two CTAs per SM (they fit by construction: <= 110 KB of stages each); if fewer were
-    // resident the kernel would still be correct, the persistent loop strides by gridDim
-    fused_step_staged_kernel<SS, DIAG><<<G.staged_grid, kStagedThreads, G.staged_smem, stream>>>(p, G.sg);
-    return cudaGetLastError();
-}
-
-template <int SS, int DIAG>
 static cudaError_t launch_fused_t(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream, int *launches)
 {
     if (G.nb_main) {
-        if (SS == 1 && G.staged) {
-            cudaError_t e = (DIAG == 1) ? launch_staged<1, 3>(p, G, stream) : launch_staged<1, DIAG>(p, G, stream);
+        if (SS == 1 && G.spec) {
+            const cudaError_t e = (cudaError_t)spec_launch(p, G.spec_first, G.spec_ntiles, stream);
             if (e != cudaSuccess) return e;
         } else {
             fused_step_kernel<SS, DIAG, true><<<G.nb_main, kFusedThreads, 0, stream>>>(p, G.main);
@@ -1155,7 +862,7 @@ int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cuda
     for (int g = 0; g < 3; ++g) {
         if (G.diag_accum) {       // every consumer warp of the persistent grid holds sums of all three grids
             R.row_begin[g] = 0;
-            R.row_end[g] = (int64_t)G.staged_grid * w;
+            R.row_end[g] = (int64_t)G.spec_grid * w;
         } else {
             R.row_begin[g] = rm;
             rm += (int64_t)nbm[g] * w;

@@ -70,8 +70,7 @@ struct OpList {
 // ---------------------------------------------------------------------------------------------
 // fused plan
 // ---------------------------------------------------------------------------------------------
-// s_* = slot of that input array in the shared-memory stage of the staged kernel (-1: not staged); arrays
-// bound to several slots of the registry (aliases) share one stage slot
+// s_* : unused since the staged generic kernel was replaced by spec_kernel.cu (kept so the plan layout is stable)
 struct FusedTType {     // one surface type on the t grid
     const double *fice, *psur, *tsur, *qatm, *tatm, *patm, *uatm, *vatm;
     const double *a_evap;    // AMOI (CCLM) or CMOI (MOM5)
@@ -135,7 +134,7 @@ struct FusedPlan {
     int diag_n;              // number of active diagnostics slots
     int prefetch_distance;   // L2 prefetch look-ahead in blocks (0 = off)
     signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index, -1 = inactive
-    int staged;              // 1: stage[] is valid and the staged (bulk copy + mbarrier) kernel may be used
+    int staged;              // specialised persistent kernel: 0 never, 1 for large grids, 2 whenever the plan fits
     int pad2;
     StageList stage[3];      // per grid: the distinct input arrays of one tile
 };
@@ -159,6 +158,10 @@ int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, c
 int64_t fused_diag_rows(const FusedPlan &plan);
 int diag_tmp_doubles(int64_t rows, int nslots);
 unsigned long long read_exact_calls();
+// specialised persistent kernel (spec_kernel.cu)
+int spec_applicable(const FusedPlan &plan, const int64_t first[3], const int ntiles[3]);
+int spec_launch(const FusedPlan &plan, const int64_t first[3], const int ntiles[3], cudaStream_t stream);
+unsigned long long read_spec_exact_calls();
 int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,
                       double *dst, int64_t n_dst, cudaStream_t stream);
