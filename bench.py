@@ -279,7 +279,8 @@ def main():
     max_size = max(m.shard_range(n_total, r, world, 512)[1] for r in range(world))
     achieved = bytes_per_cell * max_size / (kern_avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused_step_kernel", "kernel_ms": kern_avg_ms,
+                "traffic": None, "kernel": "flux_spec_kernel" if fc.info("spec_kernel") == 1 else "fused_step_kernel",
+                "kernel_ms": kern_avg_ms,
                 "algorithmic_bytes_per_cell": bytes_per_cell, "cells_per_launch": max_size, "peak_source": peak_src}
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:

@@ -281,6 +281,7 @@ extern "C" int fc_destroy(fc_context *c)
     for (int g = 1; g <= 3; ++g)
         if (c->area_owned[g]) cudaFree(c->area_dev[g]);
     cudaFree(c->diag_partials);
+    cudaFree(c->diag_counter);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->diag_buf[b]);
         if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]);
@@ -1138,51 +1139,7 @@ static bool build_fused(fc_context *c, bool do_early, bool do_normal, FusedBundl
         P.diag_n = (int)F.diag_slots.size();
         if (P.diag_n == 0) P.diag = 0;
     }
-    // stage lists of the staged kernel: the distinct input arrays of one tile, per grid
-    {
-        bool overflow = false;
-        for (int g = 0; g < 3; ++g) {
-            StageList &L = P.stage[g];
-            L.n = 0;
-            std::vector<const double *> seen;
-            auto add = [&](const double *ptr, signed char &slot) {
-                slot = -1;
-                if (!ptr) return;
-                for (size_t k = 0; k < seen.size(); ++k)
-                    if (seen[k] == ptr) {
-                        slot = (signed char)k;
-                        return;
-                    }
-                if (L.n >= kMaxStaged) {
-                    overflow = true;
-                    return;
-                }
-                slot = (signed char)L.n;
-                L.src[L.n++] = ptr;
-                seen.push_back(ptr);
-            };
-            if (g == 0) {
-                add(P.t.rsdd, P.t.s_rsdd);
-                add(P.t.bias, P.t.s_bias);
-                add(P.t.area, P.t.s_area);
-                for (int i = 0; i < c->S; ++i) {
-                    FusedTType &T = P.t.ty[i];
-                    add(T.fice, T.s_fice); add(T.psur, T.s_psur); add(T.tsur, T.s_tsur); add(T.qatm, T.s_qatm);
-                    add(T.tatm, T.s_tatm); add(T.patm, T.s_patm); add(T.uatm, T.s_uatm); add(T.vatm, T.s_vatm);
-                    add(T.a_evap, T.s_aev); add(T.a_sens, T.s_ase); add(T.qsur_in, T.s_qsur_in); add(T.fare, T.s_fare);
-                }
-            } else {
-                FusedUV &U = P.uv[g - 1];
-                add(U.area, U.s_area);
-                for (int i = 0; i < c->S; ++i) {
-                    FusedUVType &T = U.ty[i];
-                    add(T.fice, T.s_fice); add(T.psur, T.s_psur); add(T.tsur, T.s_tsur); add(T.a_mom, T.s_amom);
-                    add(T.uatm, T.s_uatm); add(T.vatm, T.s_vatm); add(T.qsur_in, T.s_qsur_in); add(T.fare, T.s_fare);
-                }
-            }
-        }
-        P.staged = overflow ? 0 : c->use_staged;
-    }
+    P.staged = c->use_staged;
     F.in_bufs.assign(ins.begin(), ins.end());
     F.out_bufs.assign(outs.begin(), outs.end());
     F.ok = true;
@@ -1322,8 +1279,20 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P)
             CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_comm[b], cudaEventDisableTiming));
         }
     if (!c->diag_host) CUDA_TRY(c, cudaHostAlloc(&c->diag_host, sizeof(double) * kDiagSlots * 3 * 2, cudaHostAllocDefault));
+    if (!c->diag_counter) {
+        CUDA_TRY(c, cudaMalloc(&c->diag_counter, sizeof(unsigned int)));
+        CUDA_TRY(c, cudaMemsetAsync(c->diag_counter, 0, sizeof(unsigned int), c->stream));
+    }
     P.diag_partials = c->diag_partials;
     P.diag_rows = rows;
+    P.diag_counter = c->diag_counter;
+    // result buffer of this step; if its previous all-reduce is still in flight on the side stream, wait for it
+    const int b = c->diag_cur ^ 1;
+    if (c->comm_busy[b]) {
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_comm[b], 0));
+        c->comm_busy[b] = false;
+    }
+    P.diag_out = c->diag_buf[b];
     return FC_OK;
 }
 
@@ -1333,16 +1302,13 @@ static double *diag_tmp(fc_context *c, const FusedPlan &P)
     return c->diag_partials + (size_t)planes * P.diag_n * (size_t)P.diag_rows;
 }
 
-// partial rows -> diag_buf[next]; if that buffer's previous all-reduce is still in flight on the side stream, wait
+// partial rows -> P.diag_out = diag_buf[next] (chosen by ensure_diag_storage); a no-op launch-wise when the specialised
+// kernel already reduced them itself
 static int finalize_diag(fc_context *c, const FusedPlan &P, const FusedBundle &F)
 {
     const int b = c->diag_cur ^ 1;
-    if (c->comm_busy[b]) {
-        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_comm[b], 0));
-        c->comm_busy[b] = false;
-    }
     int nl = 0;
-    if (launch_diag_finalize(P, diag_tmp(c, P), c->diag_buf[b], c->stream, &nl)) return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
+    if (launch_diag_finalize(P, diag_tmp(c, P), P.diag_out, c->stream, &nl)) return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
     c->launches += nl;
     c->diag_cur = b;
     c->diag_active = F.diag_slots;
@@ -1356,7 +1322,6 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     FusedPlan P = F.plan;
     if (P.t.bias) {
         P.t.bias = bias_slab(c);
-        if (P.t.s_bias >= 0) P.stage[0].src[P.t.s_bias] = P.t.bias;
     }
     bool any_host = false;
     for (int b : F.in_bufs) any_host = any_host || !c->bufs[b].user_is_device;
@@ -1527,6 +1492,11 @@ extern "C" int64_t fc_get_info(const fc_context *c, const char *name)
         return (int64_t)read_exact_calls();
     }
     if (!strcmp(name, "fused")) return (!c->dirty && c->fused[2].ok) ? 1 : 0;
+    if (!strcmp(name, "spec_kernel")) {   // fc_step_all runs on the specialised persistent kernel (spec_kernel.cu)
+        if (c->dirty || !c->fused[2].ok) return 0;
+        cudaSetDevice(c->device);
+        return fused_uses_spec(c->fused[2].plan);
+    }
     if (!strcmp(name, "fused_early")) return (!c->dirty && c->fused[0].ok) ? 1 : 0;
     if (!strcmp(name, "fused_normal")) return (!c->dirty && c->fused[1].ok) ? 1 : 0;
     if (!strcmp(name, "h2d_bytes_per_step")) return c->h2d_bytes;

@@ -116,6 +116,7 @@ struct fc_context {
     // diagnostics storage
     double *diag_partials = nullptr;
     size_t diag_partials_cap = 0;
+    unsigned int *diag_counter = nullptr;   // last-CTA-done counter of the specialised kernel
     double *diag_buf[2] = {nullptr, nullptr};   // [sum|min|max][kDiagSlots] compact slots, double buffered by step
     int diag_cur = 0;                    // buffer the last step wrote
     cudaStream_t comm_stream = nullptr;  // NCCL all-reduce runs here, overlapped with the next step

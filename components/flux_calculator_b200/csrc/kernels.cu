@@ -741,7 +741,7 @@ struct FusedGeom {
     LaunchGeom main, tail;
     int nb_main, nb_tail;
     bool spec;           // main part runs on the specialised persistent kernel (spec_kernel.cu)
-    bool diag_accum;     // ... which accumulates the diagnostics per thread: one row per consumer warp of its grid
+    bool diag_accum;     // ... which accumulates the diagnostics per thread and reduces them itself: one row per CTA
     int spec_grid;
     int64_t spec_first[3];
     int spec_ntiles[3];
@@ -796,11 +796,14 @@ static FusedGeom fused_geometry(const FusedPlan &p)
         if (G.spec_grid > 0) {
             G.spec = true;
             G.diag_accum = (p.diag != 0);
-            if (G.diag_accum) G.tail.row0 = (int64_t)G.spec_grid * (kFusedThreads / 32);
+            if (G.diag_accum) G.tail.row0 = G.spec_grid;
         }
     }
     return G;
 }
+
+// 1: the main part of this plan runs on the specialised persistent kernel, 0: on the generic fused kernel
+int fused_uses_spec(const FusedPlan &p) { return fused_geometry(p).spec ? 1 : 0; }
 
 int64_t fused_diag_rows(const FusedPlan &p)
 {
@@ -808,20 +811,36 @@ int64_t fused_diag_rows(const FusedPlan &p)
     return G.tail.row0 + (int64_t)G.nb_tail * (kFusedThreads / 32);
 }
 
+// rows of the ragged-remainder launch, per grid (the rows of the other grids' blocks are not part of a slot's sum)
+static void tail_row_ranges(const FusedGeom &G, int64_t begin[3], int64_t end[3])
+{
+    const int w = kFusedThreads / 32;
+    const int nbt[3] = {G.tail.nb_t, G.tail.nb_u, G.nb_tail - G.tail.nb_t - G.tail.nb_u};
+    int64_t rt = G.tail.row0;
+    for (int g = 0; g < 3; ++g) {
+        begin[g] = rt;
+        rt += (int64_t)nbt[g] * w;
+        end[g] = rt;
+    }
+}
+
 template <int SS, int DIAG>
 static cudaError_t launch_fused_t(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream, int *launches)
 {
+    // the ragged remainder first: the specialised kernel's last CTA folds its diagnostics rows into the result
+    if (G.nb_tail) {
+        fused_step_kernel<SS, DIAG, false><<<G.nb_tail, kFusedThreads, 0, stream>>>(p, G.tail);
+        if (launches) *launches += 1;
+    }
     if (G.nb_main) {
         if (SS == 1 && G.spec) {
-            const cudaError_t e = (cudaError_t)spec_launch(p, G.spec_first, G.spec_ntiles, stream);
+            int64_t tb[3], te[3];
+            tail_row_ranges(G, tb, te);
+            const cudaError_t e = (cudaError_t)spec_launch(p, G.spec_first, G.spec_ntiles, tb, te, stream);
             if (e != cudaSuccess) return e;
         } else {
             fused_step_kernel<SS, DIAG, true><<<G.nb_main, kFusedThreads, 0, stream>>>(p, G.main);
         }
-        if (launches) *launches += 1;
-    }
-    if (G.nb_tail) {
-        fused_step_kernel<SS, DIAG, false><<<G.nb_tail, kFusedThreads, 0, stream>>>(p, G.tail);
         if (launches) *launches += 1;
     }
     return cudaGetLastError();
@@ -853,6 +872,7 @@ int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cuda
 {
     if (!p.diag || p.diag_n <= 0) return 0;
     const FusedGeom G = fused_geometry(p);
+    if (G.spec && G.diag_accum) return 0;      // reduced in-kernel by the last CTA, diag_out is already written
     const int w = kFusedThreads / 32;
     DiagRanges R;
     memset(&R, 0, sizeof R);
@@ -860,14 +880,9 @@ int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cuda
     const int nbt[3] = {G.tail.nb_t, G.tail.nb_u, G.nb_tail - G.tail.nb_t - G.tail.nb_u};
     int64_t rm = 0, rt = G.tail.row0;
     for (int g = 0; g < 3; ++g) {
-        if (G.diag_accum) {       // every consumer warp of the persistent grid holds sums of all three grids
-            R.row_begin[g] = 0;
-            R.row_end[g] = (int64_t)G.spec_grid * w;
-        } else {
-            R.row_begin[g] = rm;
-            rm += (int64_t)nbm[g] * w;
-            R.row_end[g] = rm;
-        }
+        R.row_begin[g] = rm;
+        rm += (int64_t)nbm[g] * w;
+        R.row_end[g] = rm;
         R.tail_begin[g] = rt;
         rt += (int64_t)nbt[g] * w;
         R.tail_end[g] = rt;

@@ -91,13 +91,6 @@ struct FusedUVType {    // one surface type on the u or v grid
     signed char s_fice, s_psur, s_tsur, s_amom, s_uatm, s_vatm, s_qsur_in, s_fare;
 };
 
-constexpr int kMaxStaged = 14;      // input arrays staged per tile; more -> the direct-load kernel is used
-struct StageList {
-    int n;                          // 0: this grid / plan is not staged
-    int pad;
-    const double *src[kMaxStaged];
-};
-
 struct FusedT {
     int64_t n;
     const double *rsdd;      // RSDD of surface type 0 (null: no shortwave distribution)
@@ -129,6 +122,8 @@ struct FusedPlan {
     Consts c;
     FusedT t;
     FusedUV uv[2];           // [0] = u grid, [1] = v grid
+    double *diag_out;        // [sum|min|max][kDiagSlots] result of this step (written in-kernel by the specialised kernel)
+    unsigned int *diag_counter;   // CTAs done (last-CTA reduction of the specialised kernel); zero between launches
     double *diag_partials;   // [plane: sum|min|max][diag_n][diag_rows]
     int64_t diag_rows;       // warp rows of one fused step (row stride of the partials)
     int diag_n;              // number of active diagnostics slots
@@ -136,7 +131,6 @@ struct FusedPlan {
     signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index, -1 = inactive
     int staged;              // specialised persistent kernel: 0 never, 1 for large grids, 2 whenever the plan fits
     int pad2;
-    StageList stage[3];      // per grid: the distinct input arrays of one tile
 };
 
 // diagnostics slot layout: slot(type 0..10, quantity)
@@ -156,11 +150,13 @@ int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t st
 int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
 int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, cudaStream_t stream, int *launches);
 int64_t fused_diag_rows(const FusedPlan &plan);
+int fused_uses_spec(const FusedPlan &plan);
 int diag_tmp_doubles(int64_t rows, int nslots);
 unsigned long long read_exact_calls();
 // specialised persistent kernel (spec_kernel.cu)
 int spec_applicable(const FusedPlan &plan, const int64_t first[3], const int ntiles[3]);
-int spec_launch(const FusedPlan &plan, const int64_t first[3], const int ntiles[3], cudaStream_t stream);
+int spec_launch(const FusedPlan &plan, const int64_t first[3], const int ntiles[3], const int64_t tail_row_begin[3],
+                const int64_t tail_row_end[3], cudaStream_t stream);
 unsigned long long read_spec_exact_calls();
 int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,

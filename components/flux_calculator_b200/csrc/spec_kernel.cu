@@ -11,8 +11,10 @@
 //     slot of every array is a compile-time constant of the formula set), two cells per thread in lock step,
 //     results leave through 128-bit global stores; nothing but the running quantities lives in registers;
 //   * the formula set is a template parameter -- no method dispatch inside the kernel;
-//   * diagnostics: per-thread running sums (and min/max at level 2) over all tiles of a thread, one warp tree
-//     and one row store per quantity per kernel; the static tile schedule makes the sums reproducible;
+//   * diagnostics: per-thread running sums (and min/max at level 2) over all tiles of a thread, one warp tree per
+//     quantity per kernel, the CTA's warps combined in shared memory into one row per CTA, and the LAST CTA to
+//     finish (atomic counter) folds all rows -- and those of the ragged-remainder launch, which runs first --
+//     into the result vector: no follow-up kernel.  Static schedule + fixed trees: reproducible sums;
 //   * cells whose operands leave the range in which the lock-step division / sqrt / exp / log sequences are
 //     proven (vmath.cuh) are NOT handled inline: the warp notes the tile, and a cold, out-of-line epilogue
 //     recomputes those tiles with the IEEE routines from global memory and rebuilds the warp's diagnostics
@@ -74,10 +76,16 @@ struct SpecPlan {
     uint32_t tx_bytes[3];             // bytes one tile of that grid brings in
     const double *area[3];
     double *outq[DQ_COUNT];           // output array per diagnostics quantity (null: not produced)
-    double *partials;                 // [plane][compact slot][row]
+    double *partials;                 // [plane][compact slot][row]; rows [0, grid) are this kernel's (one per CTA)
     int64_t rows, plane;
-    int64_t row0;
+    int64_t tail_begin[3], tail_end[3];   // rows the ragged-remainder launch wrote, per grid
+    double *diag_out;                 // [sum|min|max][kDiagSlots]
+    unsigned int *counter;            // CTAs done
     signed char dmap[DQ_COUNT];       // quantity -> compact diagnostics slot (-1: inactive)
+};
+
+struct WarpSums {    // per-CTA staging of the consumer warps' diagnostics
+    double v[3][DQ_COUNT][kSpecCW];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -199,12 +207,10 @@ struct DiagAcc {    // running diagnostics of the NQ quantities Q0.. of one phas
     }
 };
 
-// warp tree + row store of one quantity (every lane calls; inactive quantities are skipped uniformly)
+// warp tree of one quantity; lane 0 leaves the warp's value in the CTA's staging area
 template <int DIAG>
-__device__ __forceinline__ void diag_flush_one(const SpecPlan &p, int q, double s, double mn, double mx, int64_t row)
+__device__ __forceinline__ void diag_flush_one(WarpSums &ws, int q, double s, double mn, double mx)
 {
-    const int cs = p.dmap[q];
-    if (cs < 0) return;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         s = add(s, __shfl_down_sync(0xffffffffu, s, off));
@@ -214,13 +220,85 @@ __device__ __forceinline__ void diag_flush_one(const SpecPlan &p, int q, double 
         }
     }
     if ((threadIdx.x & 31) == 0) {
-        double *o = p.partials + (int64_t)cs * p.rows + row;
-        o[0] = s;
+        const int w = threadIdx.x >> 5;
+        ws.v[0][q][w] = s;
         if (DIAG >= 2) {
-            o[p.plane] = mn;
-            o[2 * p.plane] = mx;
+            ws.v[1][q][w] = mn;
+            ws.v[2][q][w] = mx;
         }
     }
+}
+
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kSpecConsumers) : "memory"); }
+
+// end of kernel, consumer warps only: warps -> one row per CTA -> (last CTA) rows of all CTAs + remainder rows -> result
+template <int DIAG>
+__device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int *is_last)
+{
+    const int tid = threadIdx.x, G = gridDim.x;
+    consumer_barrier();
+    if (tid < DQ_COUNT) {
+        const int cs = p.dmap[tid];
+        if (cs >= 0) {
+            double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+#pragma unroll
+            for (int w = 0; w < kSpecCW; ++w) {
+                s = add(s, ws.v[0][tid][w]);
+                if (DIAG >= 2) {
+                    mn = fmin(mn, ws.v[1][tid][w]);
+                    mx = fmax(mx, ws.v[2][tid][w]);
+                }
+            }
+            double *o = p.partials + (int64_t)cs * p.rows + blockIdx.x;
+            o[0] = s;
+            if (DIAG >= 2) {
+                o[p.plane] = mn;
+                o[2 * p.plane] = mx;
+            }
+        }
+        __threadfence();
+    }
+    consumer_barrier();
+    if (tid == 0) *is_last = (atomicAdd(p.counter, 1u) == (unsigned)(G - 1));
+    consumer_barrier();
+    if (!*is_last) return;
+    __threadfence();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int q = warp; q < DQ_COUNT; q += kSpecCW) {      // one warp per quantity, fixed order: lane-strided rows, then a tree
+        const int cs = p.dmap[q];
+        if (cs < 0) continue;
+        const int g = (q == DQ_QSUR_U || q == DQ_UMOM) ? 1 : ((q == DQ_QSUR_V || q == DQ_VMOM) ? 2 : 0);
+        const double *col = p.partials + (int64_t)cs * p.rows;
+        double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+        for (int64_t r = lane; r < G; r += 32) {
+            s = add(s, __ldcg(col + r));
+            if (DIAG >= 2) {
+                mn = fmin(mn, __ldcg(col + p.plane + r));
+                mx = fmax(mx, __ldcg(col + 2 * p.plane + r));
+            }
+        }
+        for (int64_t r = p.tail_begin[g] + lane; r < p.tail_end[g]; r += 32) {
+            s = add(s, __ldcg(col + r));
+            if (DIAG >= 2) {
+                mn = fmin(mn, __ldcg(col + p.plane + r));
+                mx = fmax(mx, __ldcg(col + 2 * p.plane + r));
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s = add(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (DIAG >= 2) {
+                mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
+                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+            }
+        }
+        if (lane == 0) {
+            p.diag_out[0 * kDiagSlots + cs] = s;
+            p.diag_out[1 * kDiagSlots + cs] = mn;
+            p.diag_out[2 * kDiagSlots + cs] = mx;
+        }
+    }
+    if (tid == 0) *p.counter = 0u;      // ready for the next launch (same stream)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -314,7 +392,7 @@ unsigned long long read_spec_exact_calls()
 
 template <int SET, int DIAG>
 __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t j0, int64_t jstride, int ntiles, const int *flagged,
-                                             int nflag, int64_t row)
+                                             int nflag, WarpSums &ws)
 {
     const bool all = nflag > kSpecBadCap;
     for (int i = 0; i < ntiles; ++i) {
@@ -343,7 +421,7 @@ __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t 
             const int64_t j = j0 + (int64_t)i * jstride;
             diag_pair(s, mn, mx, DIAG, p.area[ph][j], p.area[ph][j + 1], x[j], x[j + 1]);
         }
-        diag_flush_one<DIAG>(p, q, s, mn, mx, row);
+        diag_flush_one<DIAG>(ws, q, s, mn, mx);
     }
 }
 
@@ -357,6 +435,8 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
     __shared__ uint64_t fullT[kSpecMaxUnits], emptyT[kSpecMaxUnits], fullU[kSpecMaxUnits], emptyU[kSpecMaxUnits];
     __shared__ int flagged[kSpecCW][kSpecBadCap];
     __shared__ int nflagged[kSpecCW];
+    __shared__ WarpSums ws;
+    __shared__ int is_last;
 
     const int NU = p.units, A = p.t_units, GT = NU / A;
     if (threadIdx.x == 0) {
@@ -370,6 +450,12 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (threadIdx.x < kSpecCW) nflagged[threadIdx.x] = 0;
+    if (DIAG)
+        for (int e = threadIdx.x; e < DQ_COUNT * kSpecCW; e += blockDim.x) {
+            (&ws.v[0][0][0])[e] = 0.0;
+            (&ws.v[1][0][0])[e] = DBL_MAX;
+            (&ws.v[2][0][0])[e] = -DBL_MAX;
+        }
     __syncthreads();
 
     // static schedule: this CTA takes positions b, b+G, b+2G, ... of the tile list [t tiles | u tiles | v tiles]
@@ -440,7 +526,6 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
     }
 
     // ---------------- consumer warps ----------------
-    const int64_t row = p.row0 + (int64_t)b * kSpecCW + warp;
     const int toff = threadIdx.x * (kSpecV * 8);
     {   // t phase
         DiagAcc<DIAG, 6, DQ_QSUR_T> dg;
@@ -474,12 +559,12 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
         __syncwarp();
         const int nf = nflagged[warp];
         if (nf) {
-            spec_cold_phase<SET, DIAG>(p, 0, j0, jstride, cnt0, flagged[warp], nf, row);
+            spec_cold_phase<SET, DIAG>(p, 0, j0, jstride, cnt0, flagged[warp], nf, ws);
             __syncwarp();
             if (lane == 0) nflagged[warp] = 0;
         } else if (DIAG) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) diag_flush_one<DIAG>(p, DQ_QSUR_T + q, dg.s[q], DIAG >= 2 ? dg.mn[q] : 0.0, DIAG >= 2 ? dg.mx[q] : 0.0, row);
+            for (int q = 0; q < 6; ++q) diag_flush_one<DIAG>(ws, DQ_QSUR_T + q, dg.s[q], DIAG >= 2 ? dg.mn[q] : 0.0, DIAG >= 2 ? dg.mx[q] : 0.0);
         }
     }
     {   // u phase, then v phase: same code, same ring
@@ -518,17 +603,18 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
             __syncwarp();
             const int nf = nflagged[warp];
             if (nf) {
-                spec_cold_phase<SET, DIAG>(p, ph, j0, jstride, cnt_ph, flagged[warp], nf, row);
+                spec_cold_phase<SET, DIAG>(p, ph, j0, jstride, cnt_ph, flagged[warp], nf, ws);
                 __syncwarp();
                 if (lane == 0) nflagged[warp] = 0;
                 __syncwarp();
             } else if (DIAG) {
                 const int q0 = north ? DQ_QSUR_V : DQ_QSUR_U;
-                diag_flush_one<DIAG>(p, q0, dg.s[0], DIAG >= 2 ? dg.mn[0] : 0.0, DIAG >= 2 ? dg.mx[0] : 0.0, row);
-                diag_flush_one<DIAG>(p, q0 + 1, dg.s[1], DIAG >= 2 ? dg.mn[1] : 0.0, DIAG >= 2 ? dg.mx[1] : 0.0, row);
+                diag_flush_one<DIAG>(ws, q0, dg.s[0], DIAG >= 2 ? dg.mn[0] : 0.0, DIAG >= 2 ? dg.mx[0] : 0.0);
+                diag_flush_one<DIAG>(ws, q0 + 1, dg.s[1], DIAG >= 2 ? dg.mn[1] : 0.0, DIAG >= 2 ? dg.mx[1] : 0.0);
             }
         }
     }
+    if (DIAG) diag_finish<DIAG>(p, ws, &is_last);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -548,7 +634,8 @@ static int spec_num_sms()
 static bool is_bulk(int m) { return m == M_CCLM || m == M_MOM5; }
 
 // ntiles[g] whole tiles starting at first[g] (decided by the caller from alignment and size)
-static bool spec_build(const FusedPlan &p, const int64_t first[3], const int ntiles[3], SpecPlan &sp, int *set_out)
+static bool spec_build(const FusedPlan &p, const int64_t first[3], const int ntiles[3], const int64_t tail_begin[3],
+                       const int64_t tail_end[3], SpecPlan &sp, int *set_out)
 {
     if (p.S != 1 || !p.do_normal) return false;
     const FusedTType &T = p.t.ty[0];
@@ -644,7 +731,12 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int nti
     sp.partials = p.diag_partials;
     sp.rows = p.diag_rows;
     sp.plane = (int64_t)p.diag_n * p.diag_rows;
-    sp.row0 = 0;
+    for (int g = 0; g < 3; ++g) {
+        sp.tail_begin[g] = tail_begin ? tail_begin[g] : 0;
+        sp.tail_end[g] = tail_end ? tail_end[g] : 0;
+    }
+    sp.diag_out = p.diag_out;
+    sp.counter = p.diag_counter;
     *set_out = set;
     return true;
 }
@@ -661,7 +753,7 @@ int spec_applicable(const FusedPlan &p, const int64_t first[3], const int ntiles
 {
     SpecPlan sp;
     int set = 0;
-    if ((int64_t)ntiles[0] + ntiles[1] + ntiles[2] <= 0 || !spec_build(p, first, ntiles, sp, &set)) return 0;
+    if ((int64_t)ntiles[0] + ntiles[1] + ntiles[2] <= 0 || !spec_build(p, first, ntiles, nullptr, nullptr, sp, &set)) return 0;
     return spec_grid(ntiles);
 }
 
@@ -681,11 +773,13 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
     return cudaGetLastError();
 }
 
-int spec_launch(const FusedPlan &p, const int64_t first[3], const int ntiles[3], cudaStream_t stream)
+int spec_launch(const FusedPlan &p, const int64_t first[3], const int ntiles[3], const int64_t tail_row_begin[3],
+                const int64_t tail_row_end[3], cudaStream_t stream)
 {
     SpecPlan sp;
     int set = 0;
-    if (!spec_build(p, first, ntiles, sp, &set)) return (int)cudaErrorInvalidValue;
+    if (!spec_build(p, first, ntiles, tail_row_begin, tail_row_end, sp, &set)) return (int)cudaErrorInvalidValue;
+    if (sp.diag && (!sp.partials || !sp.diag_out || !sp.counter)) return (int)cudaErrorInvalidValue;
     const int grid = spec_grid(ntiles);
     cudaError_t e;
     if (set == SET_BULK) {

@@ -197,3 +197,91 @@ def test_diagnostics(fcmod, level, S, n, staged):
                 assert np.isnan(mn) and np.isnan(mx)
             ref = float(np.sum(sc.area[g] * arr))
             assert abs(s - ref) <= 1e-11 * float(np.sum(np.abs(sc.area[g] * arr))), (i, g, name)
+
+
+def _diag_check(fc, sc, g_out, level):
+    for (i, g, name), arr in g_out.items():
+        if arr.size == 0:
+            continue
+        s, mn, mx = fc.diagnostics(i, g, name)
+        if level == 2:
+            assert mn == arr.min() and mx == arr.max(), (i, g, name)
+        ref = float(np.sum(sc.area[g] * arr))
+        assert abs(s - ref) <= 1e-11 * float(np.sum(np.abs(sc.area[g] * arr))), (i, g, name)
+
+
+@pytest.mark.parametrize("fset", ["CCLM", "MOM5", "RCO"])
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_spec_kernel_cold_epilogue(fcmod, fset, level):
+    """specialised persistent kernel: tiles with operands outside the proven range are recomputed by the cold
+    epilogue (IEEE routines, from global memory) and the warp's diagnostics are rebuilt from the stored outputs;
+    every other cell keeps the bits of the lock-step path (same results as the direct-load kernel)"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario(fset, n=(300000 + 37, 200000, 250000 + 511), S=1, bias=True)
+    a_t = {"CCLM": "AMOI", "MOM5": "CMOI", "RCO": "QATM"}[fset]
+    t_key = [k for k in sc.inputs if k[1] == 1 and k[2] == a_t][0]
+    sc.inputs[t_key][3] = 1e-310                     # denormal operand (t grid, first tile)
+    sc.inputs[t_key][123457] = 1e-310                # ... and a tile deep inside another CTA's schedule
+    for idx in (5, 199999):                          # u*u + v*v denormal: sqrt argument outside the proven range
+        sc.inputs[(0, 2, "UATM")][idx] = 1e-160
+        sc.inputs[(0, 2, "VATM")][idx] = 1e-160
+    sc.inputs[(0, 3, "UATM")][77777] = 1e-160
+    sc.inputs[(0, 3, "VATM")][77777] = -1e-160
+    outs = {}
+    for staged in (0, 2):
+        fc, o_out, g_out, _, _ = run_both(fcmod, sc, "device", diagnostics=level, staged=staged)
+        compare(sc, o_out, g_out)
+        if level:
+            _diag_check(fc, sc, g_out, level)
+        outs[staged] = g_out
+    assert fc.info("exact_path_calls") > 0
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[2][k], equal_nan=True), k
+
+
+def test_spec_kernel_flag_overflow(fcmod):
+    """more flagged tiles per warp than the epilogue remembers individually -> every tile of that warp is redone"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(512 * 296 * 17 + 512 * 40, 1024, 512), S=1, bias=True)
+    t_key = [k for k in sc.inputs if k[1] == 1 and k[2] == "AMOI"][0]
+    sc.inputs[t_key][::512] = 1e-310                 # one denormal operand in every tile
+    fc, o_out, g_out, _, _ = run_both(fcmod, sc, "device", diagnostics=1, staged=2)
+    compare(sc, o_out, g_out)
+    _diag_check(fc, sc, g_out, 1)
+
+
+@pytest.mark.parametrize("n", [(512, 300000, 1024), (150000, 512, 0), (1024, 1024, 400000), (152064, 152064, 152064)])
+@pytest.mark.parametrize("fset", ["MOM5", "RCO"])
+def test_spec_kernel_schedules(fcmod, n, fset):
+    """persistent schedule corner cases: CTAs without t tiles, empty grids, t->u/v ring hand-over with few tiles,
+    exactly one tile per CTA"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario(fset, n=n, S=1, bias=True)
+    _, o_out, d_out, _, _ = run_both(fcmod, sc, "device", staged=0)
+    fc, _, s_out, _, _ = run_both(fcmod, sc, "device", staged=2, diagnostics=2)
+    compare(sc, o_out, s_out)
+    _diag_check(fc, sc, s_out, 2)
+    for k in d_out:
+        assert np.array_equal(d_out[k], s_out[k], equal_nan=True), k
+
+
+def test_repeated_steps_reuse_diagnostics_buffers(fcmod):
+    """the in-kernel last-CTA reduction resets its counter: many steps in a row give the same diagnostics"""
+    from components.flux_calculator_b200 import DeviceArray
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(200000, 200000, 200000 + 3), S=1, bias=True)
+    g_in, g_out = sc.clone()
+    fc = fcmod.FluxCalculator(sc.n, sc.S)
+    fc.set_option("staged", 2)
+    sc.apply(fc, g_in, g_out, wrap=lambda a: DeviceArray.from_numpy(a))
+    for g in (1, 2, 3):
+        fc.set_area(g, sc.area[g])
+    fc.set_option("diagnostics", 2)
+    fc.prepare()
+    first = None
+    for k in range(7):
+        fc.step_all(0)
+        d = fc.diagnostics(1, 3, "VMOM")
+        if first is None:
+            first = d
+        assert d == first
