@@ -744,7 +744,7 @@ struct FusedGeom {
     bool diag_accum;     // ... which accumulates the diagnostics per thread and reduces them itself: one row per CTA
     int spec_grid;
     int64_t spec_first[3];
-    int spec_ntiles[3];
+    int64_t spec_cells[3];
 };
 
 static int num_sms()
@@ -785,18 +785,22 @@ static FusedGeom fused_geometry(const FusedPlan &p)
     G.tail.row0 = (int64_t)G.nb_main * (kFusedThreads / 32);
     G.main.prefetch_distance = p.prefetch_distance;
     G.tail.prefetch_distance = 0;
-    // specialised persistent kernel for the canonical single-surface-type plans (small grids: direct kernel)
+    // specialised persistent kernel for the canonical single-surface-type plans (small grids: direct kernel); it
+    // takes the ragged remainder along, so there is no second launch
     G.spec = false;
-    if (p.S == 1 && ((p.staged == 1 && G.nb_main >= 4 * num_sms()) || (p.staged == 2 && G.nb_main > 0))) {
+    if (al && p.S == 1 && ((p.staged == 1 && G.nb_main >= 4 * num_sms()) || (p.staged == 2 && G.nb_main + G.nb_tail > 0))) {
         for (int g = 0; g < 3; ++g) {
             G.spec_first[g] = G.main.first[g];
-            G.spec_ntiles[g] = nbm[g];
+            G.spec_cells[g] = G.main.count[g] + G.tail.count[g];
         }
-        G.spec_grid = spec_applicable(p, G.spec_first, G.spec_ntiles);
+        G.spec_grid = spec_applicable(p, G.spec_first, G.spec_cells);
         if (G.spec_grid > 0) {
             G.spec = true;
             G.diag_accum = (p.diag != 0);
-            if (G.diag_accum) G.tail.row0 = G.spec_grid;
+            G.nb_main = 1;      // one launch
+            G.nb_tail = 0;
+            G.tail.nb_t = G.tail.nb_u = 0;
+            G.tail.row0 = G.spec_grid;
         }
     }
     return G;
@@ -811,32 +815,16 @@ int64_t fused_diag_rows(const FusedPlan &p)
     return G.tail.row0 + (int64_t)G.nb_tail * (kFusedThreads / 32);
 }
 
-// rows of the ragged-remainder launch, per grid (the rows of the other grids' blocks are not part of a slot's sum)
-static void tail_row_ranges(const FusedGeom &G, int64_t begin[3], int64_t end[3])
-{
-    const int w = kFusedThreads / 32;
-    const int nbt[3] = {G.tail.nb_t, G.tail.nb_u, G.nb_tail - G.tail.nb_t - G.tail.nb_u};
-    int64_t rt = G.tail.row0;
-    for (int g = 0; g < 3; ++g) {
-        begin[g] = rt;
-        rt += (int64_t)nbt[g] * w;
-        end[g] = rt;
-    }
-}
-
 template <int SS, int DIAG>
 static cudaError_t launch_fused_t(const FusedPlan &p, const FusedGeom &G, cudaStream_t stream, int *launches)
 {
-    // the ragged remainder first: the specialised kernel's last CTA folds its diagnostics rows into the result
     if (G.nb_tail) {
         fused_step_kernel<SS, DIAG, false><<<G.nb_tail, kFusedThreads, 0, stream>>>(p, G.tail);
         if (launches) *launches += 1;
     }
     if (G.nb_main) {
         if (SS == 1 && G.spec) {
-            int64_t tb[3], te[3];
-            tail_row_ranges(G, tb, te);
-            const cudaError_t e = (cudaError_t)spec_launch(p, G.spec_first, G.spec_ntiles, tb, te, stream);
+            const cudaError_t e = (cudaError_t)spec_launch(p, G.spec_first, G.spec_cells, stream);
             if (e != cudaSuccess) return e;
         } else {
             fused_step_kernel<SS, DIAG, true><<<G.nb_main, kFusedThreads, 0, stream>>>(p, G.main);

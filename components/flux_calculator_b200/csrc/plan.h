@@ -154,9 +154,8 @@ int fused_uses_spec(const FusedPlan &plan);
 int diag_tmp_doubles(int64_t rows, int nslots);
 unsigned long long read_exact_calls();
 // specialised persistent kernel (spec_kernel.cu)
-int spec_applicable(const FusedPlan &plan, const int64_t first[3], const int ntiles[3]);
-int spec_launch(const FusedPlan &plan, const int64_t first[3], const int ntiles[3], const int64_t tail_row_begin[3],
-                const int64_t tail_row_end[3], cudaStream_t stream);
+int spec_applicable(const FusedPlan &plan, const int64_t first[3], const int64_t cells[3]);
+int spec_launch(const FusedPlan &plan, const int64_t first[3], const int64_t cells[3], cudaStream_t stream);
 unsigned long long read_spec_exact_calls();
 int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,

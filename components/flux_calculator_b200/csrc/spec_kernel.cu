@@ -20,8 +20,13 @@
 //     recomputes those tiles with the IEEE routines from global memory and rebuilds the warp's diagnostics
 //     from the stored outputs.  The hot loop carries no call, no stack frame and no spill.
 //
-// Everything else (S > 1, averaging, 'zero'/'none' mixes, misaligned arrays, early-only phase, ragged
-// remainders) runs on the generic kernels of kernels.cu, instantiated from the same formula templates.
+//   * the ragged remainder of a grid (cells mod 512) is one more tile of the schedule, taken by its CTA after
+//     the ring tiles with guarded global loads/stores -- same chain code, no second launch;
+//   * launched with programmatic stream serialisation: the next step's CTAs become resident and set up their
+//     barriers while this step drains, then wait (griddepcontrol.wait) before touching global memory.
+//
+// Everything else (S > 1, averaging, 'zero'/'none' mixes, misaligned arrays, early-only phase) runs on the
+// generic kernels of kernels.cu, instantiated from the same formula templates.
 #include "plan.h"
 
 #include <cuda_runtime.h>
@@ -62,8 +67,9 @@ enum SpecSet { SET_BULK = 0, SET_RCO = 1 };
 
 struct SpecPlan {
     Consts c;
-    int64_t first[3];                 // first cell of the tiled range on each grid
-    int ntiles[3];
+    int64_t first[3];                 // first cell of the range on each grid
+    int64_t end[3];                   // one past its last cell
+    int ntiles[3];                    // ceil(cells / tile): the last tile of a grid may be partial (guarded path)
     int units;                        // ring size in units (a multiple of t_units)
     int unit_bytes;
     int t_units;
@@ -78,7 +84,6 @@ struct SpecPlan {
     double *outq[DQ_COUNT];           // output array per diagnostics quantity (null: not produced)
     double *partials;                 // [plane][compact slot][row]; rows [0, grid) are this kernel's (one per CTA)
     int64_t rows, plane;
-    int64_t tail_begin[3], tail_end[3];   // rows the ragged-remainder launch wrote, per grid
     double *diag_out;                 // [sum|min|max][kDiagSlots]
     unsigned int *counter;            // CTAs done
     signed char dmap[DQ_COUNT];       // quantity -> compact diagnostics slot (-1: inactive)
@@ -149,6 +154,29 @@ struct StPair {
         *reinterpret_cast<double2 *>(p + j) = make_double2(x.v[0], x.v[1]);
     }
 };
+// partial tile: guarded global accesses, nv = 0, 1 or 2 valid cells
+struct LdPairGuard {
+    const double *const *src;
+    int64_t j;
+    int nv;
+    __device__ __forceinline__ S2 operator()(int slot) const
+    {
+        S2 r;
+#pragma unroll
+        for (int k = 0; k < kSpecV; ++k) r.v[k] = (k < nv) ? __ldg(src[slot] + j + k) : 1.0;
+        return r;
+    }
+};
+struct StPairGuard {
+    int64_t j;
+    int nv;
+    __device__ __forceinline__ void operator()(double *p, const S2 &x) const
+    {
+#pragma unroll
+        for (int k = 0; k < kSpecV; ++k)
+            if (k < nv) p[j + k] = x.v[k];
+    }
+};
 // cold path: one cell from global memory
 struct LdCell {
     const double *const *src;
@@ -179,6 +207,20 @@ __device__ __forceinline__ void diag_pair(double &s, double &mn, double &mx, int
     }
 }
 
+// nv valid cells (partial tile); identical to diag_pair for nv == 2
+__device__ __forceinline__ void diag_cells(double &s, double &mn, double &mx, int level, double a0, double a1, double x0, double x1, int nv)
+{
+    if (nv >= 2) {
+        diag_pair(s, mn, mx, level, a0, a1, x0, x1);
+    } else if (nv == 1) {
+        s = add(s, mul(a0, x0));
+        if (level >= 2) {
+            mn = fmin(mn, x0);
+            mx = fmax(mx, x0);
+        }
+    }
+}
+
 template <int DIAG, int NQ, int Q0>
 struct DiagAcc {    // running diagnostics of the NQ quantities Q0.. of one phase
     double s[NQ], mn[DIAG >= 2 ? NQ : 1], mx[DIAG >= 2 ? NQ : 1];
@@ -203,6 +245,23 @@ struct DiagAcc {    // running diagnostics of the NQ quantities Q0.. of one phas
         } else {
             double dm = 0.0, dM = 0.0;
             diag_pair(s[k], dm, dM, DIAG, area.v[0], area.v[1], x.v[0], x.v[1]);
+        }
+    }
+};
+
+template <int DIAG, int NQ, int Q0>
+struct DiagAccGuard {    // the same accumulators fed from a partial tile
+    DiagAcc<DIAG, NQ, Q0> &a;
+    int nv;
+    __device__ __forceinline__ void operator()(int q, const S2 &x)
+    {
+        if (DIAG == 0) return;
+        const int k = q - Q0;
+        if constexpr (DIAG >= 2) {
+            diag_cells(a.s[k], a.mn[k], a.mx[k], DIAG, a.area.v[0], a.area.v[1], x.v[0], x.v[1], nv);
+        } else {
+            double dm = 0.0, dM = 0.0;
+            diag_cells(a.s[k], dm, dM, DIAG, a.area.v[0], a.area.v[1], x.v[0], x.v[1], nv);
         }
     }
 };
@@ -267,21 +326,27 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int
     for (int q = warp; q < DQ_COUNT; q += kSpecCW) {      // one warp per quantity, fixed order: lane-strided rows, then a tree
         const int cs = p.dmap[q];
         if (cs < 0) continue;
-        const int g = (q == DQ_QSUR_U || q == DQ_UMOM) ? 1 : ((q == DQ_QSUR_V || q == DQ_VMOM) ? 2 : 0);
         const double *col = p.partials + (int64_t)cs * p.rows;
         double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-        for (int64_t r = lane; r < G; r += 32) {
-            s = add(s, __ldcg(col + r));
-            if (DIAG >= 2) {
-                mn = fmin(mn, __ldcg(col + p.plane + r));
-                mx = fmax(mx, __ldcg(col + 2 * p.plane + r));
+        constexpr int kPer = 10;      // rows per lane fetched at once (2 CTAs x 148 SMs = 296 rows -> one round)
+        for (int r0 = 0; r0 < G; r0 += 32 * kPer) {
+            double vs[kPer], vn[kPer], vx[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                const int r = r0 + k * 32 + lane;
+                vs[k] = (r < G) ? __ldcg(col + r) : 0.0;
+                if (DIAG >= 2) {
+                    vn[k] = (r < G) ? __ldcg(col + p.plane + r) : DBL_MAX;
+                    vx[k] = (r < G) ? __ldcg(col + 2 * p.plane + r) : -DBL_MAX;
+                }
             }
-        }
-        for (int64_t r = p.tail_begin[g] + lane; r < p.tail_end[g]; r += 32) {
-            s = add(s, __ldcg(col + r));
-            if (DIAG >= 2) {
-                mn = fmin(mn, __ldcg(col + p.plane + r));
-                mx = fmax(mx, __ldcg(col + 2 * p.plane + r));
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) {
+                s = add(s, vs[k]);
+                if (DIAG >= 2) {
+                    mn = fmin(mn, vn[k]);
+                    mx = fmax(mx, vx[k]);
+                }
             }
         }
 #pragma unroll
@@ -402,6 +467,7 @@ __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t 
         atomicAdd(&g_spec_exact_calls, 1ull);
         for (int k = 0; k < kSpecV; ++k) {
             const int64_t j = j0 + (int64_t)i * jstride + k;
+            if (j >= p.end[ph]) break;      // partial tile
             ExactVec<1> m;
             const LdCell ld{p.src[ph], j};
             const StCell st{j};
@@ -417,9 +483,16 @@ __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t 
         const double *x = p.outq[q];
         if (p.dmap[q] < 0 || x == nullptr) continue;      // uniform
         double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-        for (int i = 0; i < ntiles; ++i) {
+        // the hot loop's order: the partial tile (if this CTA has it: always its last) first, then the ring tiles
+        const int64_t last_start = j0 - (int64_t)threadIdx.x * kSpecV + (int64_t)(ntiles - 1) * jstride;
+        const bool has_partial = ntiles > 0 && last_start + kSpecTile > p.end[ph];
+        for (int ii = 0; ii < ntiles; ++ii) {
+            const int i = has_partial ? (ii == 0 ? ntiles - 1 : ii - 1) : ii;
             const int64_t j = j0 + (int64_t)i * jstride;
-            diag_pair(s, mn, mx, DIAG, p.area[ph][j], p.area[ph][j + 1], x[j], x[j + 1]);
+            const int64_t left = p.end[ph] - j;
+            const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
+            if (nv == 2) diag_pair(s, mn, mx, DIAG, p.area[ph][j], p.area[ph][j + 1], x[j], x[j + 1]);
+            else if (nv == 1) diag_cells(s, mn, mx, DIAG, p.area[ph][j], 0.0, x[j], 0.0, 1);
         }
         diag_flush_one<DIAG>(ws, q, s, mn, mx);
     }
@@ -457,6 +530,10 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
             (&ws.v[2][0][0])[e] = -DBL_MAX;
         }
     __syncthreads();
+    // programmatic dependent launch: everything above overlapped the previous kernel of the stream; from here on
+    // global memory is touched, so wait for that kernel to complete (no-op without the launch attribute)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // static schedule: this CTA takes positions b, b+G, b+2G, ... of the tile list [t tiles | u tiles | v tiles]
     const int G = gridDim.x, b = blockIdx.x;
@@ -474,6 +551,12 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
         sched(p.ntiles[0], p.ntiles[1], cnt1, tl1);
         sched((int64_t)p.ntiles[0] + p.ntiles[1], p.ntiles[2], cnt2, tl2);
     }
+    // the last tile of a grid may be partial: its CTA takes it after the ring tiles, through guarded global accesses
+    auto partial = [&](int ph, int cnt, int64_t tl) {
+        return cnt > 0 && tl + (int64_t)(cnt - 1) * G == p.ntiles[ph] - 1 && (p.end[ph] - p.first[ph]) % kSpecTile != 0;
+    };
+    const int part0 = partial(0, cnt0, tl0), part1 = partial(1, cnt1, tl1), part2 = partial(2, cnt2, tl2);
+    const int ring0 = cnt0 - part0, ring1 = cnt1 - part1, ring2 = cnt2 - part2;      // tiles that travel through the ring
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == kSpecCW) {
@@ -481,7 +564,7 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
         if (lane != 0) return;
         {   // t tiles: group g = i mod GT covers units [g*A, g*A + A)
             int g = 0, use = 0;
-            for (int i = 0; i < cnt0; ++i) {
+            for (int i = 0; i < ring0; ++i) {
                 if (use > 0) mbar_wait(&emptyT[g], (use - 1) & 1);
                 const int64_t cell = p.first[0] + (tl0 + (int64_t)i * G) * kSpecTile;
                 mbar_expect_tx(&fullT[g], p.tx_bytes[0]);
@@ -499,14 +582,14 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
             int h = 0, use = 0;
 #pragma unroll 1
             for (int ph = 1; ph < 3; ++ph) {
-                const int cnt_ph = ph == 1 ? cnt1 : cnt2;
+                const int cnt_ph = ph == 1 ? ring1 : ring2;
                 const int64_t tl_ph = ph == 1 ? tl1 : tl2;
                 for (int i = 0; i < cnt_ph; ++i) {
                     if (use > 0) {
                         mbar_wait(&emptyU[h], (use - 1) & 1);
                     } else {      // first use of this unit: the last t tile of the group that covered it must be done
                         const int g = h / A;
-                        const int uses_t = (cnt0 > g) ? (cnt0 - g + GT - 1) / GT : 0;
+                        const int uses_t = (ring0 > g) ? (ring0 - g + GT - 1) / GT : 0;
                         if (uses_t > 0) mbar_wait(&emptyT[g], (uses_t - 1) & 1);
                     }
                     const int64_t cell = p.first[ph] + (tl_ph + (int64_t)i * G) * kSpecTile;
@@ -531,9 +614,28 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
         DiagAcc<DIAG, 6, DQ_QSUR_T> dg;
         dg.reset();
         const int64_t j0 = p.first[0] + tl0 * kSpecTile + threadIdx.x * kSpecV, jstride = (int64_t)G * kSpecTile;
+        if (part0) {      // the partial tile first: its (slow, guarded) global loads overlap the filling of the ring
+            const int64_t j = j0 + (int64_t)(cnt0 - 1) * jstride;
+            const int64_t left = p.end[0] - j;
+            const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
+            if (DIAG) {
+                dg.area.v[0] = nv > 0 ? __ldg(p.area[0] + j) : 0.0;
+                dg.area.v[1] = nv > 1 ? __ldg(p.area[0] + j + 1) : 0.0;
+            }
+            FastVec<kSpecV> m;
+            const LdPairGuard ld{p.src[0], j, nv};
+            const StPairGuard st{j, nv};
+            DiagAccGuard<DIAG, 6, DQ_QSUR_T> dgg{dg, nv};
+            spec_t_chain<SET>(m, p, ld, st, dgg);
+            if (__any_sync(0xffffffffu, nv > 0 && m.bad()) && lane == 0) {
+                const int n = nflagged[warp];
+                if (n < kSpecBadCap) flagged[warp][n] = cnt0 - 1;
+                nflagged[warp] = n + 1;
+            }
+        }
         int g = 0, use = 0;
         int64_t j = j0;
-        for (int i = 0; i < cnt0; ++i, j += jstride) {
+        for (int i = 0; i < ring0; ++i, j += jstride) {
             if (DIAG) {
                 const double2 a = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
                 dg.area.v[0] = a.x;
@@ -574,10 +676,29 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
             DiagAcc<DIAG, 2, DQ_QSUR_U> dg;
             dg.reset();
             const int north = ph - 1;
-            const int cnt_ph = ph == 1 ? cnt1 : cnt2;
+            const int cnt_ph = ph == 1 ? cnt1 : cnt2, ring_ph = ph == 1 ? ring1 : ring2;
             const int64_t j0 = p.first[ph] + (ph == 1 ? tl1 : tl2) * kSpecTile + threadIdx.x * kSpecV, jstride = (int64_t)G * kSpecTile;
+            if (ring_ph != cnt_ph) {      // partial tile of this grid, before its ring tiles
+                const int64_t j = j0 + (int64_t)(cnt_ph - 1) * jstride;
+                const int64_t left = p.end[ph] - j;
+                const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
+                if (DIAG) {
+                    dg.area.v[0] = nv > 0 ? __ldg(p.area[ph] + j) : 0.0;
+                    dg.area.v[1] = nv > 1 ? __ldg(p.area[ph] + j + 1) : 0.0;
+                }
+                FastVec<kSpecV> m;
+                const LdPairGuard ld{p.src[ph], j, nv};
+                const StPairGuard st{j, nv};
+                DiagAccGuard<DIAG, 2, DQ_QSUR_U> dgg{dg, nv};
+                spec_uv_chain<SET>(m, p, north, ld, st, dgg);
+                if (__any_sync(0xffffffffu, nv > 0 && m.bad()) && lane == 0) {
+                    const int n = nflagged[warp];
+                    if (n < kSpecBadCap) flagged[warp][n] = cnt_ph - 1;
+                    nflagged[warp] = n + 1;
+                }
+            }
             int64_t j = j0;
-            for (int i = 0; i < cnt_ph; ++i, j += jstride) {
+            for (int i = 0; i < ring_ph; ++i, j += jstride) {
                 if (DIAG) {
                     const double2 a = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
                     dg.area.v[0] = a.x;
@@ -633,9 +754,8 @@ static int spec_num_sms()
 
 static bool is_bulk(int m) { return m == M_CCLM || m == M_MOM5; }
 
-// ntiles[g] whole tiles starting at first[g] (decided by the caller from alignment and size)
-static bool spec_build(const FusedPlan &p, const int64_t first[3], const int ntiles[3], const int64_t tail_begin[3],
-                       const int64_t tail_end[3], SpecPlan &sp, int *set_out)
+// cells[g] cells starting at first[g] (every bound array 16-byte aligned there: decided by the caller)
+static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t cells[3], SpecPlan &sp, int *set_out)
 {
     if (p.S != 1 || !p.do_normal) return false;
     const FusedTType &T = p.t.ty[0];
@@ -659,7 +779,8 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int nti
     sp.c = p.c;
     for (int g = 0; g < 3; ++g) {
         sp.first[g] = first[g];
-        sp.ntiles[g] = ntiles[g];
+        sp.end[g] = first[g] + cells[g];
+        sp.ntiles[g] = (int)((cells[g] + kSpecTile - 1) / kSpecTile);
     }
     sp.do_early = p.do_early;
     sp.has_bias = t.bias != nullptr;
@@ -731,30 +852,26 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int nti
     sp.partials = p.diag_partials;
     sp.rows = p.diag_rows;
     sp.plane = (int64_t)p.diag_n * p.diag_rows;
-    for (int g = 0; g < 3; ++g) {
-        sp.tail_begin[g] = tail_begin ? tail_begin[g] : 0;
-        sp.tail_end[g] = tail_end ? tail_end[g] : 0;
-    }
     sp.diag_out = p.diag_out;
     sp.counter = p.diag_counter;
     *set_out = set;
     return true;
 }
 
-static int spec_grid(const int ntiles[3])
+static int spec_grid(const SpecPlan &sp)
 {
-    const int64_t total = (int64_t)ntiles[0] + ntiles[1] + ntiles[2];
+    const int64_t total = (int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2];
     const int cap = 2 * spec_num_sms();
     return (int)(total < cap ? total : cap);
 }
 
-// > 0: the plan fits the specialised kernel, value = its grid size (diagnostics rows = grid * kSpecCW); 0: it does not
-int spec_applicable(const FusedPlan &p, const int64_t first[3], const int ntiles[3])
+// > 0: the plan fits the specialised kernel, value = its grid size (= diagnostics rows); 0: it does not
+int spec_applicable(const FusedPlan &p, const int64_t first[3], const int64_t cells[3])
 {
     SpecPlan sp;
     int set = 0;
-    if ((int64_t)ntiles[0] + ntiles[1] + ntiles[2] <= 0 || !spec_build(p, first, ntiles, nullptr, nullptr, sp, &set)) return 0;
-    return spec_grid(ntiles);
+    if (cells[0] + cells[1] + cells[2] <= 0 || !spec_build(p, first, cells, sp, &set)) return 0;
+    return spec_grid(sp);
 }
 
 template <int SET, int DIAG>
@@ -769,18 +886,28 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    flux_spec_kernel<SET, DIAG><<<grid, kSpecThreads, smem, stream>>>(sp);
-    return cudaGetLastError();
+    // programmatic stream serialisation: this launch may become resident while the previous kernel of the stream
+    // drains; the kernel itself waits (griddepcontrol.wait) before its first global access
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kSpecThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, flux_spec_kernel<SET, DIAG>, sp);
 }
 
-int spec_launch(const FusedPlan &p, const int64_t first[3], const int ntiles[3], const int64_t tail_row_begin[3],
-                const int64_t tail_row_end[3], cudaStream_t stream)
+int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[3], cudaStream_t stream)
 {
     SpecPlan sp;
     int set = 0;
-    if (!spec_build(p, first, ntiles, tail_row_begin, tail_row_end, sp, &set)) return (int)cudaErrorInvalidValue;
+    if (!spec_build(p, first, cells, sp, &set)) return (int)cudaErrorInvalidValue;
     if (sp.diag && (!sp.partials || !sp.diag_out || !sp.counter)) return (int)cudaErrorInvalidValue;
-    const int grid = spec_grid(ntiles);
+    const int grid = spec_grid(sp);
     cudaError_t e;
     if (set == SET_BULK) {
         if (sp.diag >= 2) e = spec_launch_t<SET_BULK, 2>(sp, grid, stream);
