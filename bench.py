@@ -50,47 +50,71 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms from a
+    thread (the timed region of the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`);
+    falls back to one `nvidia-smi` query per poll when the NVML binding is missing."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc, self.thr = index, [], None, None
+        self.index, self.rows, self.thr, self.stop_flag, self.h, self.nv = index, [], None, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            pw = float("nan")
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        names = []
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40)):
+            if r & bit:
+                names.append(name)
+        return sm, self.max_sm, pw, names
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        r = [x.strip() for x in out]
+        names = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7])
+                 if v.lower().startswith("active")]
+        return float(r[0]), float(r[1]), float(r[2]), names
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.proc = None
-            return
         def pump():
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+            while not self.stop_flag:
+                try:
+                    self.rows.append(self._poll_nvml() if self.nv else self._poll_smi())
+                except Exception:
+                    pass
+                time.sleep(0.002)
         self.thr = threading.Thread(target=pump, daemon=True)
         self.thr.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag = True
+        if self.thr:
+            self.thr.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[3]})
+        pw = [r[2] for r in self.rows if r[2] == r[2]]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(r[1] for r in self.rows),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons,
+                "how": "NVML polled every ~2 ms during the timed region" if self.nv else "nvidia-smi polled during the timed region"}
 
 
 def build_scenario(workload, offset_size=None, cells=None):
@@ -169,8 +193,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
     ap.add_argument("--cells", type=int, default=None, help="override cells per grid (debug)")

@@ -282,6 +282,7 @@ extern "C" int fc_destroy(fc_context *c)
         if (c->area_owned[g]) cudaFree(c->area_dev[g]);
     cudaFree(c->diag_partials);
     cudaFree(c->diag_counter);
+    cudaFree(c->diag_chunk_out);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->diag_buf[b]);
         if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]);
@@ -1260,18 +1261,46 @@ extern "C" int fc_average_across_surface_types(fc_context *c, int g, int idx)
 // ---------------------------------------------------------------------------------------------
 // fused steps
 // ---------------------------------------------------------------------------------------------
-static int ensure_diag_storage(fc_context *c, FusedPlan &P)
+// chunk boundaries of the host-pointer pipeline: 256-byte aligned starts, the last chunk takes the remainder
+static void chunk_range(const fc_context *c, int k, int K, int64_t c0[4], int64_t c1[4])
 {
-    const int64_t rows = fused_diag_rows(P);
+    for (int g = 1; g <= 3; ++g) {
+        c0[g] = (K == 1) ? 0 : ((c->n[g] * k / K) & ~int64_t(31));
+        c1[g] = (k == K - 1) ? c->n[g] : ((c->n[g] * (k + 1) / K) & ~int64_t(31));
+    }
+}
+
+static FusedPlan chunk_plan(const fc_context *c, const FusedPlan &P, int k, int K)
+{
+    FusedPlan Q = P;
+    if (K > 1) {
+        int64_t c0[4], c1[4];
+        chunk_range(c, k, K, c0, c1);
+        for (int g = 0; g < 3; ++g) {
+            Q.cell0[g] = c0[g + 1];
+            Q.cells[g] = c1[g + 1] - c0[g + 1];
+        }
+    }
+    return Q;
+}
+
+// Diagnostics storage for a step issued as K launches (K = 1: device-resident; K > 1: chunks of the host-pointer
+// pipeline, which run concurrently on three streams): every chunk owns its partial rows, its reduce scratch, its
+// last-CTA counter and its result vector; diag_combine folds the K vectors in chunk order into P.diag_out.
+static int ensure_diag_storage(fc_context *c, FusedPlan &P, int K)
+{
+    int64_t rows = 1;
+    for (int k = 0; k < K; ++k) rows = std::max(rows, fused_diag_rows(chunk_plan(c, P, k, K)));
     const int planes = P.diag >= 2 ? 3 : 1;
-    const size_t need = (size_t)planes * P.diag_n * (size_t)rows * sizeof(double) +
-                        (size_t)diag_tmp_doubles(rows, P.diag_n) * sizeof(double);
+    const size_t stride = (size_t)planes * P.diag_n * (size_t)rows + (size_t)diag_tmp_doubles(rows, P.diag_n);
+    const size_t need = stride * sizeof(double) * (size_t)K;
     if (need > c->diag_partials_cap) {
         cudaFree(c->diag_partials);
         c->diag_partials = nullptr;
         CUDA_TRY(c, cudaMalloc(&c->diag_partials, need));
         c->diag_partials_cap = need;
     }
+    c->diag_chunk_stride = stride;
     for (int b = 0; b < 2; ++b)
         if (!c->diag_buf[b]) {
             CUDA_TRY(c, cudaMalloc(&c->diag_buf[b], sizeof(double) * kDiagSlots * 3));
@@ -1280,8 +1309,10 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P)
         }
     if (!c->diag_host) CUDA_TRY(c, cudaHostAlloc(&c->diag_host, sizeof(double) * kDiagSlots * 3 * 2, cudaHostAllocDefault));
     if (!c->diag_counter) {
-        CUDA_TRY(c, cudaMalloc(&c->diag_counter, sizeof(unsigned int)));
-        CUDA_TRY(c, cudaMemsetAsync(c->diag_counter, 0, sizeof(unsigned int), c->stream));
+        CUDA_TRY(c, cudaMalloc(&c->diag_counter, sizeof(unsigned int) * kMaxChunks));
+        CUDA_TRY(c, cudaMemsetAsync(c->diag_counter, 0, sizeof(unsigned int) * kMaxChunks, c->stream));
+        CUDA_TRY(c, cudaMalloc(&c->diag_chunk_out, sizeof(double) * kDiagSlots * 3 * kMaxChunks));
+        CUDA_TRY(c, cudaMemsetAsync(c->diag_chunk_out, 0, sizeof(double) * kDiagSlots * 3 * kMaxChunks, c->stream));
     }
     P.diag_partials = c->diag_partials;
     P.diag_rows = rows;
@@ -1296,25 +1327,38 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P)
     return FC_OK;
 }
 
-static double *diag_tmp(fc_context *c, const FusedPlan &P)
+// chunk k's view of the diagnostics storage
+static void diag_chunk_view(const fc_context *c, const FusedPlan &P, int k, int K, FusedPlan &Q)
 {
-    const int planes = P.diag >= 2 ? 3 : 1;
-    return c->diag_partials + (size_t)planes * P.diag_n * (size_t)P.diag_rows;
+    Q.diag_partials = c->diag_partials + (size_t)k * c->diag_chunk_stride;
+    Q.diag_rows = P.diag_rows;
+    Q.diag_counter = c->diag_counter + k;
+    Q.diag_out = (K == 1) ? P.diag_out : c->diag_chunk_out + (size_t)k * 3 * kDiagSlots;
 }
 
-// partial rows -> P.diag_out = diag_buf[next] (chosen by ensure_diag_storage); a no-op launch-wise when the specialised
-// kernel already reduced them itself
-static int finalize_diag(fc_context *c, const FusedPlan &P, const FusedBundle &F)
+static double *diag_tmp(const FusedPlan &Q)
 {
-    const int b = c->diag_cur ^ 1;
+    const int planes = Q.diag >= 2 ? 3 : 1;
+    return Q.diag_partials + (size_t)planes * Q.diag_n * (size_t)Q.diag_rows;
+}
+
+// partial rows of launch Q -> Q.diag_out, on the stream Q was launched on; a no-op launch-wise when the specialised
+// kernel already reduced them itself
+static int finalize_chunk(fc_context *c, const FusedPlan &Q, cudaStream_t s)
+{
     int nl = 0;
-    if (launch_diag_finalize(P, diag_tmp(c, P), P.diag_out, c->stream, &nl)) return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
+    if (launch_diag_finalize(Q, diag_tmp(Q), Q.diag_out, s, &nl)) return fail(c, FC_ERR_CUDA, "diag finalize launch failed");
     c->launches += nl;
-    c->diag_cur = b;
+    return FC_OK;
+}
+
+// bookkeeping once the step's result vector (P.diag_out = diag_buf[next]) is issued
+static void diag_step_done(fc_context *c, const FusedPlan &P, const FusedBundle &F)
+{
+    c->diag_cur ^= 1;
     c->diag_active = F.diag_slots;
     c->diag_valid = false;
     c->diag_level = P.diag;
-    return FC_OK;
 }
 
 static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
@@ -1333,8 +1377,10 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     int nlaunch = 0;
 
     if (!any_host) {
-        if (P.diag)
-            if (int rc = ensure_diag_storage(c, P)) return rc;
+        if (P.diag) {
+            if (int rc = ensure_diag_storage(c, P, 1)) return rc;
+            diag_chunk_view(c, P, 0, 1, P);
+        }
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->profile_kernel && c->prof_used < 8192) {
             while (c->prof_ev.size() < c->prof_used + 2) {
@@ -1351,7 +1397,8 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         if (e1) CUDA_TRY(c, cudaEventRecord(e1, c->stream));
         c->launches += nlaunch;
         if (P.diag) {
-            if (int rc = finalize_diag(c, P, F)) return rc;
+            if (int rc = finalize_chunk(c, P, c->stream)) return rc;
+            diag_step_done(c, P, F);
         }
         if (!F.extra.empty())
             if (int rc = run_ops(c, F.extra)) return rc;
@@ -1361,18 +1408,15 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     // host-pointer mode: chunked H2D -> kernel -> D2H pipeline over three streams (copy engines
     // and SMs overlap; inputs of chunk k+1 travel while chunk k computes and chunk k-1 returns)
     int64_t nmax = std::max(c->n[1], std::max(c->n[2], c->n[3]));
-    int K = c->h2d_chunks > 0 ? c->h2d_chunks : (int)std::min<int64_t>(16, std::max<int64_t>(1, nmax / 262144));
-    if (P.diag) K = 1;   // keep the diagnostics partial layout simple
+    const int K = c->h2d_chunks > 0 ? std::min(c->h2d_chunks, kMaxChunks)
+                                    : (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(1, nmax / 262144));
     if (P.diag)
-        if (int rc = ensure_diag_storage(c, P)) return rc;
+        if (int rc = ensure_diag_storage(c, P, K)) return rc;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < K; ++k) {
         cudaStream_t s = c->pipe[k % 3];
         int64_t c0[4], c1[4];
-        for (int g = 1; g <= 3; ++g) {
-            c0[g] = (c->n[g] * k / K) & ~int64_t(31);          // 256-byte aligned chunk starts
-            c1[g] = (k == K - 1) ? c->n[g] : ((c->n[g] * (k + 1) / K) & ~int64_t(31));
-        }
+        chunk_range(c, k, K, c0, c1);
         for (int b : F.in_bufs) {
             const Buffer &B = c->bufs[b];
             if (B.user_is_device) continue;
@@ -1381,12 +1425,11 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
             CUDA_TRY(c, cudaMemcpyAsync(B.dev + c0[B.grid], B.user + c0[B.grid], (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, s));
             c->h2d_bytes += cnt * (int64_t)sizeof(double);
         }
-        FusedPlan Q = P;
-        for (int g = 0; g < 3; ++g) {
-            Q.cell0[g] = c0[g + 1];
-            Q.cells[g] = c1[g + 1] - c0[g + 1];
-        }
+        FusedPlan Q = chunk_plan(c, P, k, K);
+        if (P.diag) diag_chunk_view(c, P, k, K, Q);
         if (launch_fused(Q, s, &nlaunch)) return fail(c, FC_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (P.diag)
+            if (int rc = finalize_chunk(c, Q, s)) return rc;
         for (int b : F.out_bufs) {
             const Buffer &B = c->bufs[b];
             if (B.user_is_device) continue;
@@ -1399,7 +1442,11 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     c->launches += nlaunch;
     for (int k = 0; k < 3; ++k) CUDA_TRY(c, cudaStreamSynchronize(c->pipe[k]));
     if (P.diag) {
-        if (int rc = finalize_diag(c, P, F)) return rc;
+        if (K > 1) {      // fold the chunks' result vectors in chunk order
+            if (launch_diag_combine(c->diag_chunk_out, K, P.diag_out, c->stream)) return fail(c, FC_ERR_CUDA, "diag combine launch failed");
+            c->launches += 1;
+        }
+        diag_step_done(c, P, F);
     }
     if (!F.extra.empty())
         if (int rc = run_ops(c, F.extra)) return rc;

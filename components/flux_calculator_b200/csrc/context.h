@@ -49,6 +49,8 @@ struct RegridMatrix {
     double *weight = nullptr;    // device
 };
 
+constexpr int kMaxChunks = 16;   // chunks of the host-pointer pipeline
+
 enum Quantity { Q_QSUR_T = 0, Q_QSUR_U, Q_QSUR_V, Q_MEVA, Q_HLAT, Q_HSEN, Q_MOM, Q_RBBR, Q_COUNT };
 
 struct FusedBundle {
@@ -116,7 +118,9 @@ struct fc_context {
     // diagnostics storage
     double *diag_partials = nullptr;
     size_t diag_partials_cap = 0;
-    unsigned int *diag_counter = nullptr;   // last-CTA-done counter of the specialised kernel
+    unsigned int *diag_counter = nullptr;   // last-CTA-done counters of the specialised kernel, one per chunk
+    double *diag_chunk_out = nullptr;       // [kMaxChunks][sum|min|max][kDiagSlots]: per-chunk results (host-pointer pipeline)
+    size_t diag_chunk_stride = 0;           // doubles of partial rows + reduce scratch per chunk
     double *diag_buf[2] = {nullptr, nullptr};   // [sum|min|max][kDiagSlots] compact slots, double buffered by step
     int diag_cur = 0;                    // buffer the last step wrote
     cudaStream_t comm_stream = nullptr;  // NCCL all-reduce runs here, overlapped with the next step

@@ -889,6 +889,29 @@ int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cuda
     return (int)cudaGetLastError();
 }
 
+// result vectors [sum|min|max][kDiagSlots] of the chunks of one step -> one vector, in chunk order
+__global__ void diag_combine_kernel(const double *__restrict__ chunk_out, int nchunks, double *__restrict__ out)
+{
+    const int t = threadIdx.x;
+    if (t >= kDiagSlots) return;
+    double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+    for (int k = 0; k < nchunks; ++k) {
+        const double *q = chunk_out + (size_t)k * 3 * kDiagSlots;
+        s = add(s, q[t]);
+        mn = fmin(mn, q[kDiagSlots + t]);
+        mx = fmax(mx, q[2 * kDiagSlots + t]);
+    }
+    out[t] = s;
+    out[kDiagSlots + t] = mn;
+    out[2 * kDiagSlots + t] = mx;
+}
+
+int launch_diag_combine(const double *chunk_out, int nchunks, double *diag_out, cudaStream_t stream)
+{
+    diag_combine_kernel<<<1, 128, 0, stream>>>(chunk_out, nchunks, diag_out);
+    return (int)cudaGetLastError();
+}
+
 int diag_tmp_doubles(int64_t rows, int nslots) { return (int)(((rows + kDiagChunk - 1) / kDiagChunk) * nslots * 3); }
 
 int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t stream)

@@ -149,6 +149,7 @@ constexpr int kFusedCellsPerBlock = kFusedThreads * kFusedVec;
 int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t stream);
 int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
 int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, cudaStream_t stream, int *launches);
+int launch_diag_combine(const double *chunk_out, int nchunks, double *diag_out, cudaStream_t stream);
 int64_t fused_diag_rows(const FusedPlan &plan);
 int fused_uses_spec(const FusedPlan &plan);
 int diag_tmp_doubles(int64_t rows, int nslots);

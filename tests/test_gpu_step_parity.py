@@ -285,3 +285,21 @@ def test_repeated_steps_reuse_diagnostics_buffers(fcmod):
         if first is None:
             first = d
         assert d == first
+
+
+@pytest.mark.parametrize("staged", [0, 2])
+@pytest.mark.parametrize("S", [1, 2])
+def test_chunked_host_pipeline_with_diagnostics(fcmod, S, staged):
+    """host-pointer pipeline in several chunks: every chunk reduces its own diagnostics vector (concurrently, on
+    three streams), a combine kernel folds them in chunk order"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(300001, 299999, 300003), S=S, bias=True, averaging=True)
+    fc1, o_out, g1, _, _ = run_both(fcmod, sc, "host", chunks=1, diagnostics=2, staged=staged)
+    fc7, _, g7, _, _ = run_both(fcmod, sc, "host", chunks=7, diagnostics=2, staged=staged)
+    compare(sc, o_out, g7)
+    _diag_check(fc7, sc, g7, 2)
+    for k in g1:
+        assert np.array_equal(g1[k], g7[k], equal_nan=True), k
+        if g1[k].size:
+            d1, d7 = fc1.diagnostics(*k), fc7.diagnostics(*k)
+            assert d1[1:] == d7[1:] and abs(d1[0] - d7[0]) <= 1e-12 * abs(d1[0]) + 1e-300, k
