@@ -50,7 +50,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every ~2 ms from a
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every ~10 ms from a
     thread (the timed region of the default run lasts tens of milliseconds, too short for `nvidia-smi -lms`);
     falls back to one `nvidia-smi` query per poll when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -58,6 +58,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.thr, self.stop_flag, self.h, self.nv = index, [], None, False, None, None
+        self.period = 0.01      # NVML queries disturb the GPU slightly: keep them sparse
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -99,7 +100,7 @@ class ClockSampler:
                     self.rows.append(self._poll_nvml() if self.nv else self._poll_smi())
                 except Exception:
                     pass
-                time.sleep(0.002)
+                time.sleep(self.period)
         self.thr = threading.Thread(target=pump, daemon=True)
         self.thr.start()
 
@@ -114,7 +115,7 @@ class ClockSampler:
         pw = [r[2] for r in self.rows if r[2] == r[2]]
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(r[1] for r in self.rows),
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons,
-                "how": "NVML polled every ~2 ms during the timed region" if self.nv else "nvidia-smi polled during the timed region"}
+                "how": "NVML polled every ~10 ms during the timed region" if self.nv else "nvidia-smi polled during the timed region"}
 
 
 def build_scenario(workload, offset_size=None, cells=None):
@@ -206,6 +207,12 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance in blocks (tuning)")
     ap.add_argument("--staged", type=int, default=None, help="0/1: forbid/allow the staged kernel (tuning)")
+    ap.add_argument("--profile-stride", type=int, default=8,
+                    help="bracket every n-th fused launch with an event pair for the roofline's kernel time (an event between two "
+                         "launches switches their programmatic overlap off, so not every launch is bracketed)")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 diagnostics exchange: peer mailboxes written by the step's kernel over NVLink (default; falls back "
+                         "to NCCL when CUDA IPC is unavailable) or ncclAllReduce on a side stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -249,11 +256,29 @@ def main():
         fc.set_option("staged", args.staged)
     fc.prepare()
     assert fc.info("fused") == 1, "bench workload must run on the fused kernel"
+    comm_used = None
     if world > 1 and diag:
         import torch
-        uid = [m.comm_get_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        fc.comm_init(uid[0], rank, world)
+        comm_used = args.comm
+        if comm_used == "p2p":
+            hs = [None] * world
+            dist.all_gather_object(hs, fc.comm_p2p_handle())
+            try:
+                fc.comm_p2p_connect(hs, rank, world)
+                ok = 1
+            except Exception as e:      # no IPC / no peer access in this container
+                sys.stderr.write("rank %d: peer mailboxes unavailable (%s), falling back to NCCL\n" % (rank, e))
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t[0]) == 0:
+                if ok:
+                    raise SystemExit("bench.py: peer mailboxes connected on some ranks only")
+                comm_used = "nccl"
+        if comm_used == "nccl":
+            uid = [m.comm_get_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            fc.comm_init(uid[0], rank, world)
 
     def one_step(k):
         fc.step_all(600 * k)
@@ -269,7 +294,7 @@ def main():
         one_step(k)
     barrier()
     launches0 = fc.info("launches")
-    fc.set_option("profile_kernel", 1)
+    fc.set_option("profile_kernel", args.profile_stride)      # event pairs around every n-th fused launch
     sampler = ClockSampler(device)
     sampler.start()
     barrier()
@@ -401,6 +426,8 @@ def main():
             "config": {"workload": "%s: %s" % (args.workload, desc), "cells_per_grid": n_total, "formula_set": fset,
                        "surface_types": S, "bias": bias, "averaging": avg, "diagnostics": diag,
                        "parallelism": "contiguous range per GPU (fc_shard_range), %d rank(s)" % world,
+                       "diagnostics_exchange": {None: "none (1 rank)", "p2p": "peer mailboxes over NVLink, posted by the step kernel's last CTA",
+                                                "nccl": "ncclAllReduce on a side stream"}[comm_used],
                        "l2": "inputs exceed L2 (%.0f MB per step per GPU vs 126 MB), no flush" % (bytes_per_cell * max_size / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "diagnostics_sample": diag_sample, "exact_path_calls": exact_calls,

@@ -89,6 +89,8 @@ SIGNATURES = {
     "fc_get_diagnostics": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "fc_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "fc_comm_init": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_int]),
+    "fc_comm_p2p_handle": (C.c_int, [ctx_p, C.c_char_p]),
+    "fc_comm_p2p_connect": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_int]),
     "fc_allreduce_diagnostics": (C.c_int, [ctx_p]),
     "fc_set_regrid_matrix": (C.c_int, [ctx_p, C.c_int, i64, c_int32_p, c_int32_p, c_double_p]),
     "fc_regrid": (C.c_int, [ctx_p, C.c_int, dp, dp]),

@@ -13,7 +13,10 @@ using namespace fc;
 
 namespace fc {
 thread_local std::string g_last_error;
-int nccl_allreduce_diag(fc_context *ctx);   // nccl_dyn.cpp
+int nccl_allreduce_diag(fc_context *ctx);   // nccl_dyn.cu
+void p2p_destroy(fc_context *ctx);          // p2p_comm.cu
+void p2p_next_post(fc_context *ctx, PeerPost &post);
+int p2p_fetch(fc_context *ctx, double *planes, int n_active, int level);
 void nccl_destroy(fc_context *ctx);
 }  // namespace fc
 
@@ -283,6 +286,7 @@ extern "C" int fc_destroy(fc_context *c)
     cudaFree(c->diag_partials);
     cudaFree(c->diag_counter);
     cudaFree(c->diag_chunk_out);
+    p2p_destroy(c);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->diag_buf[b]);
         if (c->ev_fin[b]) cudaEventDestroy(c->ev_fin[b]);
@@ -471,7 +475,8 @@ extern "C" int fc_set_option(fc_context *c, const char *name, int64_t value)
     else if (!strcmp(name, "staged")) c->use_staged = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(name, "prefetch_distance")) c->prefetch_distance = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else if (!strcmp(name, "profile_kernel")) {
-        c->profile_kernel = value != 0;
+        c->profile_kernel = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));   // 0 off, n: every n-th launch
+        c->prof_seq = 0;
         c->prof_used = 0;
         return FC_OK;
     }
@@ -1358,6 +1363,7 @@ static void diag_step_done(fc_context *c, const FusedPlan &P, const FusedBundle 
     c->diag_cur ^= 1;
     c->diag_active = F.diag_slots;
     c->diag_valid = false;
+    c->diag_global = false;
     c->diag_level = P.diag;
 }
 
@@ -1380,9 +1386,10 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         if (P.diag) {
             if (int rc = ensure_diag_storage(c, P, 1)) return rc;
             diag_chunk_view(c, P, 0, 1, P);
+            p2p_next_post(c, P.post);      // peers connected: the kernel's last CTA posts the result to every rank
         }
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (c->profile_kernel && c->prof_used < 8192) {
+        if (c->profile_kernel && c->prof_used < 8192 && (c->prof_seq++ % c->profile_kernel) == 0) {
             while (c->prof_ev.size() < c->prof_used + 2) {
                 cudaEvent_t e;
                 CUDA_TRY(c, cudaEventCreate(&e));
@@ -1398,6 +1405,10 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         c->launches += nlaunch;
         if (P.diag) {
             if (int rc = finalize_chunk(c, P, c->stream)) return rc;
+            if (P.post.nranks > 1 && !fused_uses_spec(P)) {      // generic kernel: post with a small kernel
+                if (launch_diag_post(P.diag_out, P.post, (int)F.diag_slots.size(), c->stream)) return fail(c, FC_ERR_CUDA, "diag post launch failed");
+                c->launches += 1;
+            }
             diag_step_done(c, P, F);
         }
         if (!F.extra.empty())
@@ -1444,6 +1455,12 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     if (P.diag) {
         if (K > 1) {      // fold the chunks' result vectors in chunk order
             if (launch_diag_combine(c->diag_chunk_out, K, P.diag_out, c->stream)) return fail(c, FC_ERR_CUDA, "diag combine launch failed");
+            c->launches += 1;
+        }
+        if (c->p2p) {
+            PeerPost post;
+            p2p_next_post(c, post);
+            if (launch_diag_post(P.diag_out, post, (int)F.diag_slots.size(), c->stream)) return fail(c, FC_ERR_CUDA, "diag post launch failed");
             c->launches += 1;
         }
         diag_step_done(c, P, F);
@@ -1597,8 +1614,12 @@ int diag_fetch(fc_context *c)
         c->comm_busy[b] = false;
     }
     double *planes = c->diag_host + kDiagSlots * 3;
-    CUDA_TRY(c, cudaMemcpyAsync(planes, c->diag_buf[b], sizeof(double) * kDiagSlots * 3, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->p2p && c->diag_global) {      // global values from the peer mailboxes, folded in rank order
+        if (int rc = p2p_fetch(c, planes, (int)c->diag_active.size(), c->diag_level)) return rc;
+    } else {
+        CUDA_TRY(c, cudaMemcpyAsync(planes, c->diag_buf[b], sizeof(double) * kDiagSlots * 3, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
     for (size_t k = 0; k < c->diag_active.size(); ++k)
         for (int j = 0; j < 3; ++j) c->diag_host[c->diag_active[k] * 3 + j] = planes[j * kDiagSlots + k];
     c->diag_valid = true;
@@ -1623,6 +1644,11 @@ extern "C" int fc_allreduce_diagnostics(fc_context *c)
 {
     if (!c) return fail(nullptr, FC_ERR_ARG, "NULL context");
     if (c->diag_active.empty()) return fail(c, FC_ERR_STATE, "no diagnostics to reduce");
+    if (c->p2p) {      // the step's kernel already posted the vector to every rank: nothing to launch
+        c->diag_valid = false;
+        c->diag_global = true;
+        return FC_OK;
+    }
     if (c->nranks <= 1 || !c->nccl_comm) return FC_OK;   // single rank: local == global
     c->diag_valid = false;
     return nccl_allreduce_diag(c);

@@ -105,7 +105,7 @@ struct fc_context {
     bool pin_host = false;
     int diagnostics = 0;         // 0 off, 1 area-weighted sums, 2 sums + min/max
     int h2d_chunks = 0;          // 0 = auto
-    int use_staged = 1;          // staged (cp.async.bulk + mbarrier) kernel: 0 never, 1 for large grids, 2 whenever possible
+    int use_staged = 1;          // specialised persistent kernel (spec_kernel.cu): 0 never, >= 1 whenever the plan fits
     int prefetch_distance = 0;   // L2 prefetch look-ahead of the fused kernel, in 512-cell blocks (0 = off)
 
     // derived
@@ -134,11 +134,18 @@ struct fc_context {
     // NCCL
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory exchange (p2p_comm.cu)
+    fc::DiagMail *mailbox = nullptr;           // own mailbox [2][kMaxPeers slots, nranks used]
+    fc::DiagMail *peer_mail[fc::kMaxPeers] = {};   // every rank's mailbox as mapped here (peer_mail[rank] == mailbox)
+    bool p2p = false;                          // connected
+    unsigned long long diag_seq = 0;           // sequence number of the last step that produced diagnostics
+    bool diag_global = false;                  // fc_allreduce_diagnostics was called for the last step
 
     fc::RegridMatrix regrid[4];
 
-    // live timing of the fused kernel (option "profile_kernel"): event pairs around each launch
-    bool profile_kernel = false;
+    // live timing of the fused kernel (option "profile_kernel" = n): event pairs around every n-th launch
+    int profile_kernel = 0;
+    int64_t prof_seq = 0;
     std::vector<cudaEvent_t> prof_ev;    // start/stop pairs, recycled
     size_t prof_used = 0;
     cudaEvent_t user_ev[2] = {nullptr, nullptr};

@@ -1,0 +1,140 @@
+// p2p_comm.cu -- multi-GPU exchange of the diagnostics vector over NVLink peer memory, fused into the step.
+//
+// One process per GPU.  Every rank allocates a mailbox (2 parities x nranks DiagMail records), exports it as a CUDA
+// IPC handle; the host exchanges the handles (MPI_Allgather in the Fortran host, torch.distributed/gloo in bench.py)
+// and every rank maps all mailboxes.  From then on the last CTA of each step's kernel stores the rank's result
+// vector into the mailbox of every rank with plain peer stores, fences at system scope and publishes the step's
+// sequence number (spec_kernel.cu: diag_finish; other paths: diag_post_kernel).  No collective launch, no extra
+// kernel, nothing competing with the persistent kernel for an SM.  fc_get_diagnostics folds the nranks records in
+// rank order on the host, so all ranks see bit-identical global sums.  NCCL (nccl_dyn.cu) remains as the fallback
+// when IPC is unavailable.
+//
+// Double buffering: a record of step k is overwritten by step k+2; a reader that comes later than that gets an
+// error, never mixed data (the sequence numbers are checked before and after the copy).
+#include "context.h"
+
+#include <string.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <vector>
+
+using namespace fc;
+
+extern "C" int fc_comm_p2p_handle(fc_context *c, char handle[FC_P2P_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) <= FC_P2P_HANDLE_BYTES, "IPC handle size");
+    if (!c || !handle) return fail(c, FC_ERR_ARG, "fc_comm_p2p_handle: NULL argument");
+    cudaSetDevice(c->device);
+    if (!c->mailbox) {
+        const size_t bytes = sizeof(DiagMail) * 2 * kMaxPeers;
+        CUDA_TRY(c, cudaMalloc(&c->mailbox, bytes));
+        CUDA_TRY(c, cudaMemset(c->mailbox, 0, bytes));
+    }
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(c, cudaIpcGetMemHandle(&h, c->mailbox));
+    memset(handle, 0, FC_P2P_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof h);
+    return FC_OK;
+}
+
+extern "C" int fc_comm_p2p_connect(fc_context *c, const char *handles, int rank, int nranks)
+{
+    if (!c || !handles || nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks)
+        return fail(c, FC_ERR_ARG, "fc_comm_p2p_connect: bad argument (at most %d ranks)", kMaxPeers);
+    if (!c->mailbox) return fail(c, FC_ERR_STATE, "fc_comm_p2p_connect: call fc_comm_p2p_handle first");
+    cudaSetDevice(c->device);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            c->peer_mail[r] = c->mailbox;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * FC_P2P_HANDLE_BYTES, sizeof h);
+        void *ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            for (int q = 0; q < r; ++q)
+                if (q != rank && c->peer_mail[q]) {
+                    cudaIpcCloseMemHandle(c->peer_mail[q]);
+                    c->peer_mail[q] = nullptr;
+                }
+            return fail(c, FC_ERR_NCCL, "cudaIpcOpenMemHandle for rank %d failed: %s", r, cudaGetErrorString(e));
+        }
+        c->peer_mail[r] = (DiagMail *)ptr;
+    }
+    c->rank = rank;
+    c->nranks = nranks;
+    c->p2p = nranks > 1;
+    return FC_OK;
+}
+
+namespace fc {
+
+void p2p_destroy(fc_context *c)
+{
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (c->peer_mail[r] && c->peer_mail[r] != c->mailbox) cudaIpcCloseMemHandle(c->peer_mail[r]);
+    if (c->mailbox) cudaFree(c->mailbox);
+    c->mailbox = nullptr;
+    c->p2p = false;
+}
+
+// the PeerPost block of the step about to be issued
+void p2p_next_post(fc_context *c, PeerPost &post)
+{
+    memset(&post, 0, sizeof post);
+    if (!c->p2p) return;
+    c->diag_seq += 1;
+    post.nranks = c->nranks;
+    post.rank = c->rank;
+    post.seq = c->diag_seq;
+    post.parity = (int)(c->diag_seq & 1ull);
+    for (int r = 0; r < c->nranks; ++r) post.mail[r] = c->peer_mail[r];
+}
+
+// global diagnostics of the last step: wait until every rank's record of that step has arrived, fold in rank order
+int p2p_fetch(fc_context *c, double *planes /* [3][kDiagSlots] */, int n_active, int level)
+{
+    const int R = c->nranks, parity = (int)(c->diag_seq & 1ull);
+    std::vector<DiagMail> host((size_t)R);
+    const DiagMail *src = c->mailbox + (size_t)parity * R;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // our own record is posted
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        CUDA_TRY(c, cudaMemcpy(host.data(), src, sizeof(DiagMail) * R, cudaMemcpyDeviceToHost));
+        bool all = true;
+        for (int r = 0; r < R; ++r) {
+            if (host[r].seq > c->diag_seq)
+                return fail(c, FC_ERR_STATE, "diagnostics of step %llu were overwritten: rank %d is already at step %llu "
+                            "(read the global diagnostics at most one step late)", c->diag_seq, r, host[r].seq);
+            all = all && host[r].seq == c->diag_seq;
+        }
+        if (all) break;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0)
+            return fail(c, FC_ERR_NCCL, "peer diagnostics of step %llu did not arrive within 30 s", c->diag_seq);
+        usleep(20);
+    }
+    // every sequence number was seen BEFORE this copy started, so the records it reads are complete
+    CUDA_TRY(c, cudaMemcpy(host.data(), src, sizeof(DiagMail) * R, cudaMemcpyDeviceToHost));
+    for (int r = 0; r < R; ++r)
+        if (host[r].seq != c->diag_seq)
+            return fail(c, FC_ERR_STATE, "diagnostics of step %llu were overwritten while being read", c->diag_seq);
+    for (int k = 0; k < n_active; ++k) {
+        double s = 0.0, mn = host[0].v[1][k], mx = host[0].v[2][k];
+        for (int r = 0; r < R; ++r) {
+            s += host[r].v[0][k];
+            if (level >= 2) {
+                mn = host[r].v[1][k] < mn ? host[r].v[1][k] : mn;
+                mx = host[r].v[2][k] > mx ? host[r].v[2][k] : mx;
+            }
+        }
+        planes[0 * kDiagSlots + k] = s;
+        planes[1 * kDiagSlots + k] = mn;
+        planes[2 * kDiagSlots + k] = mx;
+    }
+    return FC_OK;
+}
+
+}  // namespace fc

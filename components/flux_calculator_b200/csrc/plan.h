@@ -112,6 +112,24 @@ struct FusedUV {
     FusedUVType ty[kMaxSurfaceTypes];
 };
 
+// Peer-memory exchange of the diagnostics (p2p_comm.cu): every rank owns a mailbox [parity][source rank] of DiagMail
+// records; the last CTA of a step's kernel stores the rank's result vector into the mailbox of EVERY rank over
+// NVLink (plain peer stores), fences, and publishes the step's sequence number.  Readers fold the records in rank
+// order, so all ranks obtain bit-identical global values.
+constexpr int kMaxPeers = 16;
+constexpr int kDiagSlotsFwd = (kMaxSurfaceTypes + 1) * 10;
+struct DiagMail {
+    double v[3][kDiagSlotsFwd];      // [sum|min|max][compact slot]
+    unsigned long long seq;          // step sequence number, written last (release, system scope)
+    unsigned long long pad;
+};
+struct PeerPost {
+    int nranks, rank;                // nranks <= 1: off
+    int parity, pad;
+    unsigned long long seq;
+    DiagMail *mail[kMaxPeers];       // mailbox base of every rank (the own one included), mapped into this process
+};
+
 struct FusedPlan {
     int S;                   // num_surface_types
     int do_early;            // RBBR (+ its average) in this launch
@@ -122,6 +140,7 @@ struct FusedPlan {
     Consts c;
     FusedT t;
     FusedUV uv[2];           // [0] = u grid, [1] = v grid
+    PeerPost post;           // in-kernel peer exchange of the result vector (specialised kernel, device-resident step)
     double *diag_out;        // [sum|min|max][kDiagSlots] result of this step (written in-kernel by the specialised kernel)
     unsigned int *diag_counter;   // CTAs done (last-CTA reduction of the specialised kernel); zero between launches
     double *diag_partials;   // [plane: sum|min|max][diag_n][diag_rows]
@@ -129,13 +148,14 @@ struct FusedPlan {
     int diag_n;              // number of active diagnostics slots
     int prefetch_distance;   // L2 prefetch look-ahead in blocks (0 = off)
     signed char diag_map[(kMaxSurfaceTypes + 1) * 10];   // slot -> compact index, -1 = inactive
-    int staged;              // specialised persistent kernel: 0 never, 1 for large grids, 2 whenever the plan fits
+    int staged;              // specialised persistent kernel: 0 never, >= 1 whenever the plan fits
     int pad2;
 };
 
 // diagnostics slot layout: slot(type 0..10, quantity)
 enum DiagQuantity { DQ_QSUR_T = 0, DQ_MEVA, DQ_HLAT, DQ_HSEN, DQ_RBBR, DQ_RSDR, DQ_QSUR_U, DQ_UMOM, DQ_QSUR_V, DQ_VMOM, DQ_COUNT };
 constexpr int kDiagSlots = (kMaxSurfaceTypes + 1) * DQ_COUNT;
+static_assert(kDiagSlots == kDiagSlotsFwd, "DiagMail layout");
 
 constexpr int kFusedThreads = 256;
 #ifndef FC_MIN_BLOCKS
@@ -149,6 +169,7 @@ constexpr int kFusedCellsPerBlock = kFusedThreads * kFusedVec;
 int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t stream);
 int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
 int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, cudaStream_t stream, int *launches);
+int launch_diag_post(const double *diag_out, const PeerPost &post, int n_active, cudaStream_t stream);
 int launch_diag_combine(const double *chunk_out, int nchunks, double *diag_out, cudaStream_t stream);
 int64_t fused_diag_rows(const FusedPlan &plan);
 int fused_uses_spec(const FusedPlan &plan);

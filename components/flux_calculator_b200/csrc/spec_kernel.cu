@@ -86,6 +86,7 @@ struct SpecPlan {
     int64_t rows, plane;
     double *diag_out;                 // [sum|min|max][kDiagSlots]
     unsigned int *counter;            // CTAs done
+    PeerPost post;                    // peer mailboxes (multi-GPU): the last CTA also posts the result there
     signed char dmap[DQ_COUNT];       // quantity -> compact diagnostics slot (-1: inactive)
 };
 
@@ -361,7 +362,23 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int
             p.diag_out[0 * kDiagSlots + cs] = s;
             p.diag_out[1 * kDiagSlots + cs] = mn;
             p.diag_out[2 * kDiagSlots + cs] = mx;
+            // compute -> exchange in one kernel: the result goes straight into every rank's mailbox over NVLink
+            for (int r = 0; r < p.post.nranks; ++r) {
+                DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
+                m->v[0][cs] = s;
+                m->v[1][cs] = mn;
+                m->v[2][cs] = mx;
+            }
         }
+    }
+    if (p.post.nranks > 1) {
+        __threadfence_system();          // the records are visible system-wide before ...
+        consumer_barrier();
+        if (tid == 0)
+            for (int r = 0; r < p.post.nranks; ++r) {      // ... the sequence number that publishes them
+                DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&m->seq), "l"(p.post.seq) : "memory");
+            }
     }
     if (tid == 0) *p.counter = 0u;      // ready for the next launch (same stream)
 }
@@ -854,6 +871,8 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     sp.plane = (int64_t)p.diag_n * p.diag_rows;
     sp.diag_out = p.diag_out;
     sp.counter = p.diag_counter;
+    sp.post = p.post;
+    if (!p.diag || sp.post.nranks <= 1) sp.post.nranks = 0;
     *set_out = set;
     return true;
 }

@@ -176,6 +176,18 @@ class FluxCalculator:
     def comm_init(self, unique_id, rank, nranks):
         self._check(lib.fc_comm_init(self._ctx, unique_id, rank, nranks))
 
+    def comm_p2p_handle(self):
+        """CUDA IPC handle of this rank's diagnostics mailbox (64 bytes); all-gather them and call comm_p2p_connect"""
+        buf = C.create_string_buffer(64)
+        self._check(lib.fc_comm_p2p_handle(self._ctx, buf))
+        return buf.raw
+
+    def comm_p2p_connect(self, handles, rank, nranks):
+        """handles: the ranks' 64-byte handles in rank order; afterwards every step posts its diagnostics to all ranks"""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * nranks
+        self._check(lib.fc_comm_p2p_connect(self._ctx, blob, rank, nranks))
+
     def allreduce_diagnostics(self):
         self._check(lib.fc_allreduce_diagnostics(self._ctx))
 

@@ -253,7 +253,8 @@ fc_stream_t fc_get_stream(fc_context *ctx);
 
 /* CUDA-event timing on the context's stream: record event `which` (0 = start, 1 = stop); elapsed
  * waits for event 1.  fc_kernel_time_ms returns the summed device time and the number of fused-kernel
- * launches bracketed by event pairs since the last call (needs option "profile_kernel" = 1). */
+ * launches bracketed by event pairs since the last call (needs option "profile_kernel" = n >= 1: every n-th
+ * fused launch is bracketed; an event between two launches disables their programmatic overlap). */
 int fc_event_record(fc_context *ctx, int which);
 int fc_event_elapsed_ms(fc_context *ctx, double *ms);
 int fc_kernel_time_ms(fc_context *ctx, double *total_ms, int64_t *count);
@@ -261,7 +262,8 @@ int fc_kernel_time_ms(fc_context *ctx, double *total_ms, int64_t *count);
 /* options: "force_generic" (0/1: use the op-list interpreter kernels instead of the fused kernel),
  *          "pin_host" (0/1: cudaHostRegister bound host arrays), "h2d_chunks" (pipeline depth of the
  *          host-pointer path), "diagnostics" (0 off, 1 area-weighted sums, 2 sums + min/max),
- *          "profile_kernel" (0/1), "staged" (0/1: allow the shared-memory staged kernel, default 1),
+ *          "profile_kernel" (0 off, n: time every n-th fused launch), "staged" (specialised persistent kernel: 0 never,
+ *          >= 1 (default) whenever the plan fits),
  *          "prefetch_distance" (L2 prefetch look-ahead of the direct kernel in 512-cell blocks, default 0) */
 int fc_set_option(fc_context *ctx, const char *name, int64_t value);
 int64_t fc_get_info(const fc_context *ctx, const char *name);
@@ -283,6 +285,17 @@ int fc_get_diagnostics(fc_context *ctx, int surface_type, int grid, int var_idx,
 int fc_comm_get_unique_id(char id[FC_UNIQUE_ID_BYTES]);                  /* ncclGetUniqueId */
 int fc_comm_init(fc_context *ctx, const char id[FC_UNIQUE_ID_BYTES], int rank, int nranks);
 int fc_allreduce_diagnostics(fc_context *ctx);                           /* ncclAllReduce sum / min / max */
+
+/* Peer-memory exchange fused into the step (preferred on one NVLink/NVSwitch node, one process per GPU): every
+ * rank exports its mailbox (fc_comm_p2p_handle), the host all-gathers the handles (MPI_Allgather of
+ * FC_P2P_HANDLE_BYTES per rank) and passes the rank-ordered array to fc_comm_p2p_connect.  From then on the last
+ * CTA of every step's kernel stores the rank's diagnostics vector into the mailbox of every rank over NVLink;
+ * fc_allreduce_diagnostics launches nothing, and fc_get_diagnostics folds the ranks' records in rank order
+ * (bit-identical on all ranks).  The global values of a step can be read until two further steps were issued.
+ * If fc_comm_p2p_connect fails (no IPC / no peer access) use fc_comm_init (NCCL) instead. */
+#define FC_P2P_HANDLE_BYTES 64
+int fc_comm_p2p_handle(fc_context *ctx, char handle[FC_P2P_HANDLE_BYTES]);
+int fc_comm_p2p_connect(fc_context *ctx, const char *handles /* nranks x FC_P2P_HANDLE_BYTES */, int rank, int nranks);
 
 /* ------------------------------------------------------------------------------------------------
  * "Next" row: do_regridding (flux_calculator_basic.F90:463-522), COO sparse mat-vec with the
