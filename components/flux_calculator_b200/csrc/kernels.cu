@@ -747,17 +747,6 @@ struct FusedGeom {
     int64_t spec_cells[3];
 };
 
-static int num_sms()
-{
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
-
 static FusedGeom fused_geometry(const FusedPlan &p)
 {
     FusedGeom G;

@@ -154,6 +154,19 @@ module fluxcalc_c_api
       character(kind=c_char), intent(in) :: id(128)
       integer(c_int), value :: rank, nranks
     end function
+    ! peer-memory exchange fused into the step (one process per GPU on one NVLink node): export the mailbox handle,
+    ! MPI_Allgather the 64-byte handles, connect; afterwards every step posts its diagnostics to all ranks
+    integer(c_int) function fc_comm_p2p_handle(ctx, handle) bind(c, name='fc_comm_p2p_handle')
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(out) :: handle(64)
+    end function
+    integer(c_int) function fc_comm_p2p_connect(ctx, handles, rank, nranks) bind(c, name='fc_comm_p2p_connect')
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(in) :: handles(*)     ! nranks x 64 bytes, rank order
+      integer(c_int), value :: rank, nranks
+    end function
     integer(c_int) function fc_allreduce_diagnostics(ctx) bind(c, name='fc_allreduce_diagnostics')
       import :: c_ptr, c_int
       type(c_ptr), value :: ctx
