@@ -774,10 +774,10 @@ static FusedGeom fused_geometry(const FusedPlan &p)
     G.tail.row0 = (int64_t)G.nb_main * (kFusedThreads / 32);
     G.main.prefetch_distance = p.prefetch_distance;
     G.tail.prefetch_distance = 0;
-    // specialised persistent kernel for the canonical single-surface-type plans, whatever the grid size (20 000 cells:
+    // specialised persistent kernel for the canonical plans with one or two surface types, whatever the grid size (20 000 cells:
     // 6 us per step against 20 us on the generic kernels); it takes the ragged remainder along: one launch
     G.spec = false;
-    if (al && p.S == 1 && p.staged >= 1 && G.nb_main + G.nb_tail > 0) {
+    if (al && p.S <= 2 && p.staged >= 1 && G.nb_main + G.nb_tail > 0) {
         for (int g = 0; g < 3; ++g) {
             G.spec_first[g] = G.main.first[g];
             G.spec_cells[g] = G.main.count[g] + G.tail.count[g];
@@ -812,7 +812,7 @@ static cudaError_t launch_fused_t(const FusedPlan &p, const FusedGeom &G, cudaSt
         if (launches) *launches += 1;
     }
     if (G.nb_main) {
-        if (SS == 1 && G.spec) {
+        if (G.spec) {
             const cudaError_t e = (cudaError_t)spec_launch(p, G.spec_first, G.spec_cells, stream);
             if (e != cudaSuccess) return e;
         } else {

@@ -1,31 +1,33 @@
-// spec_kernel.cu -- the fast path of the fused coupling step: one persistent, formula-set-specialised kernel
-// for single-surface-type canonical configurations (every configuration BASELINE.json benchmarks with S = 1).
+// spec_kernel.cu -- the fast path of the fused coupling step: one persistent, formula-set-specialised kernel for
+// the canonical configurations with one or two surface types (every configuration BASELINE.json benchmarks).
 //
-//   * persistent CTAs (two per SM), each one producer warp + kSpecCW consumer warps;
+//   * persistent CTAs: one producer warp + TEAMS x 8 consumer warps.  One surface type: 2 CTAs per SM, one team
+//     each.  Two surface types (15-16 input arrays per t tile): 1 CTA per SM with two teams that share one ring, so
+//     that three 60 KB stages serve two tiles in work and one in flight;
 //   * the producer streams the input arrays of 512-cell tiles into a shared-memory ring with cp.async.bulk,
-//     completion counted on mbarriers; the ring is carved in UNITS: a t-grid tile (11-12 arrays) takes
-//     t_units consecutive units, a u/v-grid tile (2-6 arrays) takes one, so the light u/v tiles get twice (bulk
-//     set) or five times (RCO set) as many stages as the t tiles out of the same bytes, and the switch from t
-//     tiles to u/v tiles needs no drain (the first use of a unit waits for the last t tile that covered it);
-//   * consumers read operands from shared memory at the point of use (LDS.128 with an immediate offset: the
-//     slot of every array is a compile-time constant of the formula set), two cells per thread in lock step,
-//     results leave through 128-bit global stores; nothing but the running quantities lives in registers;
-//   * the formula set is a template parameter -- no method dispatch inside the kernel;
+//     completion counted on mbarriers.  The ring bytes are carved twice: into t stages (all arrays of a t-grid
+//     tile) and into smaller u/v stages, so the light u/v tiles get about twice as many stages out of the same
+//     bytes; the switch from t tiles to u/v tiles needs no drain (the first use of a u/v stage waits for the last
+//     t tile of every t stage it overlaps);
+//   * consumers read operands from shared memory at the point of use (LDS.128 with an immediate offset: the slot
+//     of every array is a compile-time constant of the formula set), two cells per thread in lock step, results
+//     leave through 128-bit global stores; nothing but the running quantities lives in registers;
+//   * formula set and number of surface types are template parameters -- no method dispatch inside the kernel;
+//     area-fraction averages over the surface types (average_across_surface_types) are formed in registers;
 //   * diagnostics: per-thread running sums (and min/max at level 2) over all tiles of a thread, one warp tree per
 //     quantity per kernel, the CTA's warps combined in shared memory into one row per CTA, and the LAST CTA to
-//     finish (atomic counter) folds all rows -- and those of the ragged-remainder launch, which runs first --
-//     into the result vector: no follow-up kernel.  Static schedule + fixed trees: reproducible sums;
+//     finish (atomic counter) folds all rows into the result vector and posts it to the peer GPUs' mailboxes over
+//     NVLink: no follow-up kernel, no collective launch.  Static schedule + fixed trees: reproducible sums;
 //   * cells whose operands leave the range in which the lock-step division / sqrt / exp / log sequences are
 //     proven (vmath.cuh) are NOT handled inline: the warp notes the tile, and a cold, out-of-line epilogue
 //     recomputes those tiles with the IEEE routines from global memory and rebuilds the warp's diagnostics
-//     from the stored outputs.  The hot loop carries no call, no stack frame and no spill.
-//
-//   * the ragged remainder of a grid (cells mod 512) is one more tile of the schedule, taken by its CTA after
+//     from the stored outputs.  The hot loop carries no call, no stack frame and no spill;
+//   * the ragged remainder of a grid (cells mod 512) is one more tile of the schedule, taken by its CTA before
 //     the ring tiles with guarded global loads/stores -- same chain code, no second launch;
 //   * launched with programmatic stream serialisation: the next step's CTAs become resident and set up their
 //     barriers while this step drains, then wait (griddepcontrol.wait) before touching global memory.
 //
-// Everything else (S > 1, averaging, 'zero'/'none' mixes, misaligned arrays, early-only phase) runs on the
+// Everything else (S > 2, 'zero'/'none' mixes, averaged QSUR, misaligned arrays, early-only phase) runs on the
 // generic kernels of kernels.cu, instantiated from the same formula templates.
 #include "plan.h"
 
@@ -36,63 +38,83 @@
 namespace fc {
 
 constexpr int kSpecV = 2;
-constexpr int kSpecCW = kFusedThreads / 32;              // consumer warps: one 512-cell tile per pass
-constexpr int kSpecConsumers = kSpecCW * 32;
-constexpr int kSpecThreads = kSpecConsumers + 32;        // + producer warp
-constexpr int kSpecTile = kSpecConsumers * kSpecV;
+constexpr int kTeamWarps = kFusedThreads / 32;           // consumer warps of one team: one 512-cell tile per pass
+constexpr int kTeamThreads = kTeamWarps * 32;
+constexpr int kSpecTile = kTeamThreads * kSpecV;
 constexpr int kSpecSlotBytes = kSpecTile * 8;            // one array of one tile
-constexpr int kSpecMaxUnits = 16;
-constexpr int kSpecMaxSlots = 12;
+constexpr int kSpecMaxStages = 16;
+constexpr int kSpecMaxBars = 32;                         // barriers per set: lcm(teams, stages) <= 2 * 16
+constexpr int kSpecMaxSlots = 16;
+constexpr int kSpecMaxNS = 2;                            // surface types the specialised kernel handles
 constexpr int kSpecBadCap = 16;                          // flagged tiles remembered per warp and phase; more -> all
-static_assert(kSpecTile == kFusedCellsPerBlock, "the ragged-remainder launch assumes the same tile size");
+static_assert(kSpecTile == kFusedCellsPerBlock, "tile size is shared with the generic kernels' geometry");
 
 using S2 = Vd<kSpecV>;
 
-// slots of the shared-memory stage, per formula set
-namespace bulk {    // CCLM / MOM5 formulae (the MOM5 routines forward to the CCLM ones, flux_mass_evap.F90:107-115)
-enum { FICE = 0, PSUR, TSUR, QATM, TATM, UATM, VATM, AEV, PATM, RSDD, BIAS, ASE /* MOM5: CHEA != CMOI */, NT };
-enum { U_FICE = 0, U_PSUR, U_TSUR, U_UATM, U_VATM, U_AMOM, NUV };
-constexpr int kUnitSlots = 6, kTUnits = 2;
-}  // namespace bulk
-namespace rco {     // Meier et al. 1999 formulae; QSUR on the t grid is still the CCLM routine (App. F-1)
-enum { FICE = 0, PSUR, TSUR, QATM, TATM, UATM, VATM, RSDD, BIAS, NT };
-enum { U_UATM = 0, U_VATM, NUV };
-constexpr int kUnitSlots = 2, kTUnits = 5;
-}  // namespace rco
-static_assert(bulk::NT <= bulk::kUnitSlots * bulk::kTUnits && bulk::NUV <= bulk::kUnitSlots, "");
-static_assert(rco::NT <= rco::kUnitSlots * rco::kTUnits && rco::NUV <= rco::kUnitSlots, "");
-static_assert(bulk::NT <= kSpecMaxSlots && rco::NT <= kSpecMaxSlots, "");
-
 enum SpecSet { SET_BULK = 0, SET_RCO = 1 };
+
+// Slots of the shared-memory stage: shared (atmosphere / bottom-model) arrays first, then the per-surface-type
+// arrays (FICE, TSUR and, with two types, FARE), then the MOM5-only second transfer coefficient.
+//   SET_BULK: CCLM / MOM5 formulae (the MOM5 routines forward to the CCLM ones, flux_mass_evap.F90:107-115)
+//   SET_RCO : Meier et al. 1999 formulae; QSUR on the t grid is still the CCLM routine (App. F-1)
+template <int SET, int NS>
+struct Lay {
+    static constexpr int kPer = (NS == 1) ? 2 : 3;       // per-type arrays: FICE, TSUR (, FARE)
+    // t grid
+    static constexpr int PSUR = 0, QATM = 1, TATM = 2, UATM = 3, VATM = 4, RSDD = 5, BIAS = 6;
+    static constexpr int AEV = 7, PATM = 8;              // bulk only
+    static constexpr int kShared = (SET == SET_BULK) ? 9 : 7;
+    __host__ __device__ static constexpr int FICE(int i) { return kShared + kPer * i; }
+    __host__ __device__ static constexpr int TSUR(int i) { return kShared + kPer * i + 1; }
+    __host__ __device__ static constexpr int FARE(int i) { return kShared + kPer * i + 2; }
+    static constexpr int ASE = kShared + kPer * NS;      // bulk/MOM5 only (CHEA != CMOI)
+    static constexpr int NT = ASE + (SET == SET_BULK ? 1 : 0);
+    // u / v grid
+    static constexpr int U_UATM = 0, U_VATM = 1, U_PSUR = 2, U_AMOM = 3;
+    static constexpr int kUShared = (SET == SET_BULK) ? 4 : 2;
+    __host__ __device__ static constexpr int U_FICE(int i) { return kUShared + kPer * i; }       // bulk only
+    __host__ __device__ static constexpr int U_TSUR(int i) { return kUShared + kPer * i + 1; }   // bulk only
+    __host__ __device__ static constexpr int U_FARE(int i) { return (SET == SET_BULK) ? kUShared + kPer * i + 2 : kUShared + i; }
+    static constexpr int NUV = (SET == SET_BULK) ? kUShared + kPer * NS : kUShared + (NS == 1 ? 0 : NS);
+};
+static_assert(Lay<SET_BULK, 2>::NT <= kSpecMaxSlots && Lay<SET_BULK, 1>::NT == 12 && Lay<SET_BULK, 1>::NUV == 6, "");
 
 struct SpecPlan {
     Consts c;
     int64_t first[3];                 // first cell of the range on each grid
     int64_t end[3];                   // one past its last cell
     int ntiles[3];                    // ceil(cells / tile): the last tile of a grid may be partial (guarded path)
-    int units;                        // ring size in units (a multiple of t_units)
-    int unit_bytes;
-    int t_units;
+    int t_stages, u_stages;           // the two carvings of the ring
+    int t_stage_bytes, u_stage_bytes;
+    int t_bars, u_bars;               // lcm(teams, stages): tile i uses barrier i mod bars (one per (team, stage) pair) in phase i / bars
     int do_early;                     // RBBR in this launch
     int has_bias, has_rsdr;
+    int any_avg_t;                    // some t-grid flux is area-fraction averaged (FARE is staged)
     int ase_slot;                     // bulk: slot of the sensible-heat transfer coefficient (AEV for CCLM, ASE for MOM5)
     int diag;
-    double latent_heat;
+    int ns;
+    double latent_heat[kSpecMaxNS];
     const double *src[3][kSpecMaxSlots];   // per grid: source array of each stage slot (null: slot unused)
     uint32_t tx_bytes[3];             // bytes one tile of that grid brings in
     const double *area[3];
-    double *outq[DQ_COUNT];           // output array per diagnostics quantity (null: not produced)
+    double *out[kSpecMaxNS + 1][DQ_COUNT];   // [surface type, 0 = average][quantity] (null: not produced)
     double *partials;                 // [plane][compact slot][row]; rows [0, grid) are this kernel's (one per CTA)
     int64_t rows, plane;
     double *diag_out;                 // [sum|min|max][kDiagSlots]
     unsigned int *counter;            // CTAs done
     PeerPost post;                    // peer mailboxes (multi-GPU): the last CTA also posts the result there
-    signed char dmap[DQ_COUNT];       // quantity -> compact diagnostics slot (-1: inactive)
+    signed char dmap[(kSpecMaxNS + 1) * DQ_COUNT];   // type * DQ_COUNT + quantity -> compact diagnostics slot (-1: inactive)
 };
 
+template <int NS, int DIAG>
 struct WarpSums {    // per-CTA staging of the consumer warps' diagnostics
-    double v[3][DQ_COUNT][kSpecCW];
+    static constexpr int kWarps = (NS == 1 ? 1 : 2) * kTeamWarps;
+    static constexpr int kSlots = (NS == 1 ? 1 : NS + 1) * DQ_COUNT;
+    double v[DIAG >= 2 ? 3 : 1][kSlots][kWarps];
 };
+// staging index of (surface type, quantity): with one type only that type's quantities exist
+template <int NS>
+__device__ __forceinline__ constexpr int ws_index(int type, int q) { return NS == 1 ? q : type * DQ_COUNT + q; }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / bulk-copy primitives (PTX ISA: mbarrier, cp.async.bulk)
@@ -195,7 +217,7 @@ struct StCell {
 };
 struct NoDiag {
     template <class T>
-    __device__ __forceinline__ void operator()(int, const T &) const {}
+    __device__ __forceinline__ void operator()(int, int, const T &) const {}
 };
 
 // acc = acc + (area0*x0 + area1*x1): the one definition both the hot loop and the rebuild of the cold epilogue use
@@ -207,7 +229,6 @@ __device__ __forceinline__ void diag_pair(double &s, double &mn, double &mx, int
         mx = fmax(fmax(mx, x0), x1);
     }
 }
-
 // nv valid cells (partial tile); identical to diag_pair for nv == 2
 __device__ __forceinline__ void diag_cells(double &s, double &mn, double &mx, int level, double a0, double a1, double x0, double x1, int nv)
 {
@@ -222,25 +243,32 @@ __device__ __forceinline__ void diag_cells(double &s, double &mn, double &mx, in
     }
 }
 
-template <int DIAG, int NQ, int Q0>
-struct DiagAcc {    // running diagnostics of the NQ quantities Q0.. of one phase
-    double s[NQ], mn[DIAG >= 2 ? NQ : 1], mx[DIAG >= 2 ? NQ : 1];
+// running diagnostics of one phase: NQ quantities (Q0 ..) of every surface type (and of the averages with two types)
+template <int NS, int DIAG, int NQ, int Q0>
+struct DiagAcc {
+    static constexpr int kTypes = (NS == 1) ? 1 : NS + 1;
+    static constexpr int kN = kTypes * NQ;
+    double s[kN], mn[DIAG >= 2 ? kN : 1], mx[DIAG >= 2 ? kN : 1];
     S2 area;
+    int nv;      // valid cells of the tile being accumulated (2 except in the partial tile)
+    static __device__ __forceinline__ constexpr int idx(int type, int q) { return (NS == 1 ? 0 : type * NQ) + (q - Q0); }
     __device__ __forceinline__ void reset()
     {
+        nv = kSpecV;
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            s[q] = 0.0;
+        for (int k = 0; k < kN; ++k) {
+            s[k] = 0.0;
             if (DIAG >= 2) {
-                mn[q] = DBL_MAX;
-                mx[q] = -DBL_MAX;
+                mn[k] = DBL_MAX;
+                mx[k] = -DBL_MAX;
             }
         }
     }
-    __device__ __forceinline__ void operator()(int q, const S2 &x)
+    // full tile
+    __device__ __forceinline__ void operator()(int type, int q, const S2 &x)
     {
         if (DIAG == 0) return;
-        const int k = q - Q0;
+        const int k = idx(type, q);
         if constexpr (DIAG >= 2) {
             diag_pair(s[k], mn[k], mx[k], DIAG, area.v[0], area.v[1], x.v[0], x.v[1]);
         } else {
@@ -249,15 +277,14 @@ struct DiagAcc {    // running diagnostics of the NQ quantities Q0.. of one phas
         }
     }
 };
-
-template <int DIAG, int NQ, int Q0>
+template <int NS, int DIAG, int NQ, int Q0>
 struct DiagAccGuard {    // the same accumulators fed from a partial tile
-    DiagAcc<DIAG, NQ, Q0> &a;
+    DiagAcc<NS, DIAG, NQ, Q0> &a;
     int nv;
-    __device__ __forceinline__ void operator()(int q, const S2 &x)
+    __device__ __forceinline__ void operator()(int type, int q, const S2 &x)
     {
         if (DIAG == 0) return;
-        const int k = q - Q0;
+        const int k = DiagAcc<NS, DIAG, NQ, Q0>::idx(type, q);
         if constexpr (DIAG >= 2) {
             diag_cells(a.s[k], a.mn[k], a.mx[k], DIAG, a.area.v[0], a.area.v[1], x.v[0], x.v[1], nv);
         } else {
@@ -268,8 +295,8 @@ struct DiagAccGuard {    // the same accumulators fed from a partial tile
 };
 
 // warp tree of one quantity; lane 0 leaves the warp's value in the CTA's staging area
-template <int DIAG>
-__device__ __forceinline__ void diag_flush_one(WarpSums &ws, int q, double s, double mn, double mx)
+template <int NS, int DIAG>
+__device__ __forceinline__ void diag_flush_one(WarpSums<NS, DIAG> &ws, int wsi, double s, double mn, double mx)
 {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -281,30 +308,36 @@ __device__ __forceinline__ void diag_flush_one(WarpSums &ws, int q, double s, do
     }
     if ((threadIdx.x & 31) == 0) {
         const int w = threadIdx.x >> 5;
-        ws.v[0][q][w] = s;
-        if (DIAG >= 2) {
-            ws.v[1][q][w] = mn;
-            ws.v[2][q][w] = mx;
+        ws.v[0][wsi][w] = s;
+        if constexpr (DIAG >= 2) {
+            ws.v[1][wsi][w] = mn;
+            ws.v[2][wsi][w] = mx;
         }
     }
 }
 
-__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kSpecConsumers) : "memory"); }
-
-// end of kernel, consumer warps only: warps -> one row per CTA -> (last CTA) rows of all CTAs + remainder rows -> result
-template <int DIAG>
-__device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int *is_last)
+template <int NS>
+__device__ __forceinline__ void consumer_barrier()
 {
+    asm volatile("bar.sync 1, %0;" ::"n"((NS == 1 ? 1 : 2) * kTeamThreads) : "memory");
+}
+
+// end of kernel, consumer warps only: warps -> one row per CTA -> (last CTA) rows of all CTAs -> result (+ peer mailboxes)
+template <int NS, int DIAG>
+__device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums<NS, DIAG> &ws, int *is_last)
+{
+    constexpr int kWarps = WarpSums<NS, DIAG>::kWarps;
+    constexpr int kSlots = WarpSums<NS, DIAG>::kSlots;
     const int tid = threadIdx.x, G = gridDim.x;
-    consumer_barrier();
-    if (tid < DQ_COUNT) {
-        const int cs = p.dmap[tid];
+    consumer_barrier<NS>();
+    if (tid < kSlots) {
+        const int cs = p.dmap[NS == 1 ? DQ_COUNT + tid : tid];      // one type: staging holds surface type 1
         if (cs >= 0) {
             double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
 #pragma unroll
-            for (int w = 0; w < kSpecCW; ++w) {
+            for (int w = 0; w < kWarps; ++w) {
                 s = add(s, ws.v[0][tid][w]);
-                if (DIAG >= 2) {
+                if constexpr (DIAG >= 2) {
                     mn = fmin(mn, ws.v[1][tid][w]);
                     mx = fmax(mx, ws.v[2][tid][w]);
                 }
@@ -318,14 +351,14 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int
         }
         __threadfence();
     }
-    consumer_barrier();
+    consumer_barrier<NS>();
     if (tid == 0) *is_last = (atomicAdd(p.counter, 1u) == (unsigned)(G - 1));
-    consumer_barrier();
+    consumer_barrier<NS>();
     if (!*is_last) return;
     __threadfence();
     const int warp = tid >> 5, lane = tid & 31;
-    for (int q = warp; q < DQ_COUNT; q += kSpecCW) {      // one warp per quantity, fixed order: lane-strided rows, then a tree
-        const int cs = p.dmap[q];
+    for (int q = warp; q < kSlots; q += kWarps) {      // one warp per quantity, fixed order: lane-strided rows, then a tree
+        const int cs = p.dmap[NS == 1 ? DQ_COUNT + q : q];
         if (cs < 0) continue;
         const double *col = p.partials + (int64_t)cs * p.rows;
         double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
@@ -373,7 +406,7 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int
     }
     if (p.post.nranks > 1) {
         __threadfence_system();          // the records are visible system-wide before ...
-        consumer_barrier();
+        consumer_barrier<NS>();
         if (tid == 0)
             for (int r = 0; r < p.post.nranks; ++r) {      // ... the sequence number that publishes them
                 DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
@@ -386,82 +419,120 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums &ws, int
 // ---------------------------------------------------------------------------------------------
 // the chains, written once over (arithmetic policy, operand source, result sink, diagnostics sink)
 // ---------------------------------------------------------------------------------------------
-// t grid: QSUR -> MEVA (+bias) -> HLAT, HSEN, RBBR, RSDR.  Call-site wiring of calculate.F90 (App. A.2): the evaporation
-// routine gets TATM in its temperature slot (:87), the sensible-heat routine gets QATM in its q_s slot (:178).
-template <int SET, class M, class LD, class ST, class DG>
+// acc = acc + x*fare, separate multiply and add (average_across_surface_types, calculate.F90:379-382)
+template <class M>
+__device__ __forceinline__ void avg_add(typename M::T &acc, const typename M::T &x, const typename M::T &fare)
+{
+    acc = M::add(acc, M::mul(x, fare));
+}
+
+// t grid, per surface type: QSUR -> MEVA (+bias) -> HLAT, HSEN, RBBR, RSDR; then the type-0 averages.
+// Call-site wiring of calculate.F90 (App. A.2): the evaporation routine gets TATM in its temperature slot (:87), the
+// sensible-heat routine gets QATM in its q_s slot (:178).
+template <int SET, int NS, class M, class LD, class ST, class DG>
 __device__ __forceinline__ void spec_t_chain(M &m, const SpecPlan &p, const LD &ld, const ST &st, DG &dg)
 {
     using T = typename M::T;
+    using L = Lay<SET, NS>;
     const Consts &c = p.c;
-    constexpr int FICE = SET == SET_BULK ? (int)bulk::FICE : (int)rco::FICE, PSUR = SET == SET_BULK ? (int)bulk::PSUR : (int)rco::PSUR,
-                  TSUR = SET == SET_BULK ? (int)bulk::TSUR : (int)rco::TSUR, QATM = SET == SET_BULK ? (int)bulk::QATM : (int)rco::QATM,
-                  TATM = SET == SET_BULK ? (int)bulk::TATM : (int)rco::TATM, UATM = SET == SET_BULK ? (int)bulk::UATM : (int)rco::UATM,
-                  VATM = SET == SET_BULK ? (int)bulk::VATM : (int)rco::VATM, RSDD = SET == SET_BULK ? (int)bulk::RSDD : (int)rco::RSDD,
-                  BIAS = SET == SET_BULK ? (int)bulk::BIAS : (int)rco::BIAS;
-    // calc_spec_vapor_surface (calculate.F90:25-50)
-    const T qsur = spec_vapor_surface_cclm(m, ld(FICE), ld(PSUR), ld(TSUR), c);
-    st(p.outq[DQ_QSUR_T], qsur);
-    dg(DQ_QSUR_T, qsur);
-    const T vel = wind_speed(m, ld(UATM), ld(VATM));
-    // calc_flux_mass_evap (calculate.F90:54-120) + bias (:112-116)
-    T meva;
-    if (SET == SET_BULK) meva = flux_mass_evap_cclm(m, ld(bulk::AEV), ld(PSUR), ld(QATM), qsur, ld(TATM), vel, c);
-    else meva = flux_mass_evap_rco(m, ld(QATM), ld(TSUR), vel);
-    if (p.has_bias) meva = M::add(meva, ld(BIAS));
-    st(p.outq[DQ_MEVA], meva);
-    dg(DQ_MEVA, meva);
-    // calc_flux_heat_latent (calculate.F90:124-154): the corrected MEVA
-    const T hlat = M::mul(meva, M::bc(p.latent_heat));
-    st(p.outq[DQ_HLAT], hlat);
-    dg(DQ_HLAT, hlat);
-    // calc_flux_heat_sensible (calculate.F90:156-208)
-    T hsen;
-    if (SET == SET_BULK) hsen = flux_heat_sensible_cclm(m, ld(p.ase_slot), ld(bulk::PATM), ld(PSUR), ld(QATM), ld(TATM), ld(TSUR), vel, c);
-    else hsen = flux_heat_sensible_rco<M>(ld(TATM), ld(TSUR), vel);
-    st(p.outq[DQ_HSEN], hsen);
-    dg(DQ_HSEN, hsen);
-    // calc_flux_radiation_blackbody (calculate.F90:320-345), early phase
-    if (p.do_early) {
-        const T rbbr = flux_radiation_blackbody_StBo<M>(ld(TSUR), c.stefan_boltzmann_constant);
-        st(p.outq[DQ_RBBR], rbbr);
-        dg(DQ_RBBR, rbbr);
+    const T vel = wind_speed(m, ld(L::UATM), ld(L::VATM));
+    T aM = M::bc(0.0), aL = M::bc(0.0), aH = M::bc(0.0), aR = M::bc(0.0), aS = M::bc(0.0);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int ty = i + 1;
+        // calc_spec_vapor_surface (calculate.F90:25-50)
+        const T qsur = spec_vapor_surface_cclm(m, ld(L::FICE(i)), ld(L::PSUR), ld(L::TSUR(i)), c);
+        st(p.out[ty][DQ_QSUR_T], qsur);
+        dg(ty, DQ_QSUR_T, qsur);
+        // calc_flux_mass_evap (calculate.F90:54-120) + bias (:112-116)
+        T meva;
+        if (SET == SET_BULK) meva = flux_mass_evap_cclm(m, ld(L::AEV), ld(L::PSUR), ld(L::QATM), qsur, ld(L::TATM), vel, c);
+        else meva = flux_mass_evap_rco(m, ld(L::QATM), ld(L::TSUR(i)), vel);
+        if (p.has_bias) meva = M::add(meva, ld(L::BIAS));
+        st(p.out[ty][DQ_MEVA], meva);
+        dg(ty, DQ_MEVA, meva);
+        // calc_flux_heat_latent (calculate.F90:124-154): the corrected MEVA
+        const T hlat = M::mul(meva, M::bc(p.latent_heat[i]));
+        st(p.out[ty][DQ_HLAT], hlat);
+        dg(ty, DQ_HLAT, hlat);
+        // calc_flux_heat_sensible (calculate.F90:156-208)
+        T hsen;
+        if (SET == SET_BULK)
+            hsen = flux_heat_sensible_cclm(m, ld(p.ase_slot), ld(L::PATM), ld(L::PSUR), ld(L::QATM), ld(L::TATM), ld(L::TSUR(i)), vel, c);
+        else
+            hsen = flux_heat_sensible_rco<M>(ld(L::TATM), ld(L::TSUR(i)), vel);
+        st(p.out[ty][DQ_HSEN], hsen);
+        dg(ty, DQ_HSEN, hsen);
+        T fare;
+        if (NS > 1 && p.any_avg_t) {
+            fare = ld(L::FARE(i));
+            if (p.out[0][DQ_MEVA]) avg_add<M>(aM, meva, fare);
+            if (p.out[0][DQ_HLAT]) avg_add<M>(aL, hlat, fare);
+            if (p.out[0][DQ_HSEN]) avg_add<M>(aH, hsen, fare);
+        }
+        // calc_flux_radiation_blackbody (calculate.F90:320-345), early phase
+        if (p.do_early) {
+            const T rbbr = flux_radiation_blackbody_StBo<M>(ld(L::TSUR(i)), c.stefan_boltzmann_constant);
+            st(p.out[ty][DQ_RBBR], rbbr);
+            dg(ty, DQ_RBBR, rbbr);
+            if (NS > 1 && p.out[0][DQ_RBBR]) avg_add<M>(aR, rbbr, fare);
+        }
+        // distribute_shortwave_radiation_flux (calculate.F90:347-364): a copy
+        if (p.has_rsdr) {
+            const T rsdr = ld(L::RSDD);
+            st(p.out[ty][DQ_RSDR], rsdr);
+            dg(ty, DQ_RSDR, rsdr);
+            if (NS > 1 && p.out[0][DQ_RSDR]) avg_add<M>(aS, rsdr, fare);
+        }
     }
-    // distribute_shortwave_radiation_flux (calculate.F90:347-364): a copy
-    if (p.has_rsdr) {
-        const T rsdr = ld(RSDD);
-        st(p.outq[DQ_RSDR], rsdr);
-        dg(DQ_RSDR, rsdr);
+    if (NS > 1) {      // average_across_surface_types (calculate.F90:368-385) of the sent fluxes
+        if (p.out[0][DQ_MEVA]) { st(p.out[0][DQ_MEVA], aM); dg(0, DQ_MEVA, aM); }
+        if (p.out[0][DQ_HLAT]) { st(p.out[0][DQ_HLAT], aL); dg(0, DQ_HLAT, aL); }
+        if (p.out[0][DQ_HSEN]) { st(p.out[0][DQ_HSEN], aH); dg(0, DQ_HSEN, aH); }
+        if (p.do_early && p.out[0][DQ_RBBR]) { st(p.out[0][DQ_RBBR], aR); dg(0, DQ_RBBR, aR); }
+        if (p.has_rsdr && p.out[0][DQ_RSDR]) { st(p.out[0][DQ_RSDR], aS); dg(0, DQ_RSDR, aS); }
     }
 }
 
 // u / v grid: QSUR on that grid (bulk sets) -> momentum flux, east component on the u grid, north on the v grid
-template <int SET, class M, class LD, class ST, class DG>
+template <int SET, int NS, class M, class LD, class ST, class DG>
 __device__ __forceinline__ void spec_uv_chain(M &m, const SpecPlan &p, int north, const LD &ld, const ST &st, DG &dg)
 {
     using T = typename M::T;
+    using L = Lay<SET, NS>;
     const Consts &c = p.c;
     const int qQ = north ? DQ_QSUR_V : DQ_QSUR_U, qM = north ? DQ_VMOM : DQ_UMOM;
-    if (SET == SET_BULK) {
-        const T qsur = spec_vapor_surface_cclm(m, ld(bulk::U_FICE), ld(bulk::U_PSUR), ld(bulk::U_TSUR), c);
-        st(p.outq[qQ], qsur);
-        dg(DQ_QSUR_U, qsur);      // phase-local index: DiagAcc of the u/v phase starts at DQ_QSUR_U for both grids
-        const T vel = wind_speed(m, ld(bulk::U_UATM), ld(bulk::U_VATM));
-        const T fa = momentum_flux_air_cclm(m, ld(bulk::U_AMOM), ld(bulk::U_PSUR), qsur, ld(bulk::U_TSUR), vel, c);
-        const T mom = momentum_component<M>(fa, ld(north ? (int)bulk::U_VATM : (int)bulk::U_UATM));
-        st(p.outq[qM], mom);
-        dg(DQ_UMOM, mom);
-    } else {
-        const T vel = wind_speed(m, ld(rco::U_UATM), ld(rco::U_VATM));
-        const T fa = momentum_flux_air_rco<M>(vel);
-        const T mom = momentum_component<M>(fa, ld(north ? (int)rco::U_VATM : (int)rco::U_UATM));
-        st(p.outq[qM], mom);
-        dg(DQ_UMOM, mom);
+    const T vel = wind_speed(m, ld(L::U_UATM), ld(L::U_VATM));
+    const T wind = ld(north ? L::U_VATM : L::U_UATM);
+    T aM = M::bc(0.0);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int ty = i + 1;
+        T mom;
+        if (SET == SET_BULK) {
+            const T qsur = spec_vapor_surface_cclm(m, ld(L::U_FICE(i)), ld(L::U_PSUR), ld(L::U_TSUR(i)), c);
+            st(p.out[ty][qQ], qsur);
+            dg(ty, DQ_QSUR_U, qsur);      // phase-local index: the u/v accumulators start at DQ_QSUR_U for both grids
+            const T fa = momentum_flux_air_cclm(m, ld(L::U_AMOM), ld(L::U_PSUR), qsur, ld(L::U_TSUR(i)), vel, c);
+            mom = momentum_component<M>(fa, wind);
+        } else {
+            mom = momentum_component<M>(momentum_flux_air_rco<M>(vel), wind);
+        }
+        st(p.out[ty][qM], mom);
+        dg(ty, DQ_UMOM, mom);
+        if (NS > 1 && p.out[0][qM]) avg_add<M>(aM, mom, ld(L::U_FARE(i)));
+    }
+    if (NS > 1 && p.out[0][qM]) {
+        st(p.out[0][qM], aM);
+        dg(0, DQ_UMOM, aM);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // cold epilogue of one phase of one warp: recompute the flagged tiles with the IEEE routines (scalar, from global
-// memory), then rebuild this warp's diagnostics of the phase from the stored outputs in the hot loop's order.
+// memory), then rebuild this warp's diagnostics of the phase from the stored outputs in the hot loop's order:
+// the partial tile (jpart >= 0) first, then the ring tiles j0, j0 + jstride, ...
+// flagged[]: ring-tile numbers, -1 = the partial tile.
 // ---------------------------------------------------------------------------------------------
 __device__ unsigned long long g_spec_exact_calls = 0ull;
 
@@ -472,80 +543,101 @@ unsigned long long read_spec_exact_calls()
     return v;
 }
 
-template <int SET, int DIAG>
-__device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t j0, int64_t jstride, int ntiles, const int *flagged,
-                                             int nflag, WarpSums &ws)
+template <int SET, int NS>
+__device__ __forceinline__ void spec_fix_pair(const SpecPlan &p, int ph, int64_t j)
+{
+    atomicAdd(&g_spec_exact_calls, 1ull);
+    for (int k = 0; k < kSpecV; ++k) {
+        if (j + k >= p.end[ph]) break;      // partial tile
+        ExactVec<1> m;
+        const LdCell ld{p.src[ph], j + k};
+        const StCell st{j + k};
+        NoDiag nd;
+        if (ph == 0) spec_t_chain<SET, NS>(m, p, ld, st, nd);
+        else spec_uv_chain<SET, NS>(m, p, ph - 1, ld, st, nd);
+    }
+}
+
+template <int SET, int NS, int DIAG>
+__device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t jpart, int64_t j0, int64_t jstride, int ntiles,
+                                             const int *flagged, int nflag, WarpSums<NS, DIAG> &ws)
 {
     const bool all = nflag > kSpecBadCap;
-    for (int i = 0; i < ntiles; ++i) {
+    for (int i = -1; i < ntiles; ++i) {
+        if (i < 0 && jpart < 0) continue;
         bool f = all;
         for (int e = 0; e < nflag && e < kSpecBadCap; ++e) f = f || (flagged[e] == i);
-        if (!f) continue;
-        atomicAdd(&g_spec_exact_calls, 1ull);
-        for (int k = 0; k < kSpecV; ++k) {
-            const int64_t j = j0 + (int64_t)i * jstride + k;
-            if (j >= p.end[ph]) break;      // partial tile
-            ExactVec<1> m;
-            const LdCell ld{p.src[ph], j};
-            const StCell st{j};
-            NoDiag nd;
-            if (ph == 0) spec_t_chain<SET>(m, p, ld, st, nd);
-            else spec_uv_chain<SET>(m, p, ph - 1, ld, st, nd);
-        }
+        if (f) spec_fix_pair<SET, NS>(p, ph, i < 0 ? jpart : j0 + (int64_t)i * jstride);
     }
     if (DIAG == 0) return;
     const int q0 = (ph == 0) ? DQ_QSUR_T : (ph == 1 ? DQ_QSUR_U : DQ_QSUR_V);
     const int nq = (ph == 0) ? 6 : 2;
-    for (int q = q0; q < q0 + nq; ++q) {
-        const double *x = p.outq[q];
-        if (p.dmap[q] < 0 || x == nullptr) continue;      // uniform
-        double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-        // the hot loop's order: the partial tile (if this CTA has it: always its last) first, then the ring tiles
-        const int64_t last_start = j0 - (int64_t)threadIdx.x * kSpecV + (int64_t)(ntiles - 1) * jstride;
-        const bool has_partial = ntiles > 0 && last_start + kSpecTile > p.end[ph];
-        for (int ii = 0; ii < ntiles; ++ii) {
-            const int i = has_partial ? (ii == 0 ? ntiles - 1 : ii - 1) : ii;
-            const int64_t j = j0 + (int64_t)i * jstride;
-            const int64_t left = p.end[ph] - j;
-            const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
-            if (nv == 2) diag_pair(s, mn, mx, DIAG, p.area[ph][j], p.area[ph][j + 1], x[j], x[j + 1]);
-            else if (nv == 1) diag_cells(s, mn, mx, DIAG, p.area[ph][j], 0.0, x[j], 0.0, 1);
+    for (int ty = (NS == 1 ? 1 : 0); ty <= NS; ++ty)
+        for (int q = q0; q < q0 + nq; ++q) {
+            const double *x = p.out[ty][q];
+            if (p.dmap[ty * DQ_COUNT + q] < 0 || x == nullptr) continue;      // uniform
+            double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+            for (int i = -1; i < ntiles; ++i) {
+                if (i < 0 && jpart < 0) continue;
+                const int64_t j = i < 0 ? jpart : j0 + (int64_t)i * jstride;
+                const int64_t left = p.end[ph] - j;
+                const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
+                if (nv == 2) diag_pair(s, mn, mx, DIAG, p.area[ph][j], p.area[ph][j + 1], x[j], x[j + 1]);
+                else if (nv == 1) diag_cells(s, mn, mx, DIAG, p.area[ph][j], 0.0, x[j], 0.0, 1);
+            }
+            diag_flush_one<NS, DIAG>(ws, ws_index<NS>(ty, q), s, mn, mx);
         }
-        diag_flush_one<DIAG>(ws, q, s, mn, mx);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int SET, int DIAG>
-__global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid_constant__ SpecPlan p)
+template <int NS>
+struct SpecGeom {
+    static constexpr int kTeams = (NS == 1) ? 1 : 2;
+    static constexpr int kConsumers = kTeams * kTeamThreads;
+    static constexpr int kThreads = kConsumers + 32;         // + producer warp
+    static constexpr int kWarps = kTeams * kTeamWarps;
+    static constexpr int kCtasPerSm = (NS == 1) ? 2 : 1;
+};
+
+template <int SET, int NS, int DIAG>
+__global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPerSm) flux_spec_kernel(const __grid_constant__ SpecPlan p)
 {
+    using GEO = SpecGeom<NS>;
+    constexpr int TEAMS = GEO::kTeams;
     extern __shared__ __align__(128) char ring[];
-    __shared__ uint64_t fullT[kSpecMaxUnits], emptyT[kSpecMaxUnits], fullU[kSpecMaxUnits], emptyU[kSpecMaxUnits];
-    __shared__ int flagged[kSpecCW][kSpecBadCap];
-    __shared__ int nflagged[kSpecCW];
-    __shared__ WarpSums ws;
+    // Tile i of a phase lives in stage i mod NT and is consumed by team i mod TEAMS.  With two teams alternating on a
+    // stage each team would skip every other phase of a per-stage barrier, which mbarrier parity cannot tell apart; so
+    // there is one barrier per (team, stage) pair: index i mod LT (LT = lcm(TEAMS, NT)), phase i / LT.
+    __shared__ uint64_t fullT[kSpecMaxBars], emptyT[kSpecMaxBars], fullU[kSpecMaxBars], emptyU[kSpecMaxBars];
+    __shared__ int flagged[GEO::kWarps][kSpecBadCap];
+    __shared__ int nflagged[GEO::kWarps];
+    __shared__ WarpSums<NS, DIAG> ws;
     __shared__ int is_last;
 
-    const int NU = p.units, A = p.t_units, GT = NU / A;
+    const int NT = p.t_stages, NUS = p.u_stages, LT = p.t_bars, LU = p.u_bars;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NU; ++s) {
-            mbar_init(&fullT[s], 1);             // one expect_tx arrival + the bytes
-            mbar_init(&emptyT[s], kSpecCW);      // one arrival per consumer warp
+        for (int s = 0; s < kSpecMaxBars; ++s) {
+            mbar_init(&fullT[s], 1);                // one expect_tx arrival + the bytes
+            mbar_init(&emptyT[s], kTeamWarps);      // one arrival per consumer warp of the team that took the tile
             mbar_init(&fullU[s], 1);
-            mbar_init(&emptyU[s], kSpecCW);
+            mbar_init(&emptyU[s], kTeamWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (threadIdx.x < kSpecCW) nflagged[threadIdx.x] = 0;
-    if (DIAG)
-        for (int e = threadIdx.x; e < DQ_COUNT * kSpecCW; e += blockDim.x) {
+    if (threadIdx.x < GEO::kWarps) nflagged[threadIdx.x] = 0;
+    if (DIAG) {
+        constexpr int kE = WarpSums<NS, DIAG>::kSlots * WarpSums<NS, DIAG>::kWarps;
+        for (int e = threadIdx.x; e < kE; e += blockDim.x) {
             (&ws.v[0][0][0])[e] = 0.0;
-            (&ws.v[1][0][0])[e] = DBL_MAX;
-            (&ws.v[2][0][0])[e] = -DBL_MAX;
+            if constexpr (DIAG >= 2) {
+                (&ws.v[1][0][0])[e] = DBL_MAX;
+                (&ws.v[2][0][0])[e] = -DBL_MAX;
+            }
         }
+    }
     __syncthreads();
     // programmatic dependent launch: everything above overlapped the previous kernel of the stream; from here on
     // global memory is touched, so wait for that kernel to complete (no-op without the launch attribute)
@@ -568,7 +660,7 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
         sched(p.ntiles[0], p.ntiles[1], cnt1, tl1);
         sched((int64_t)p.ntiles[0] + p.ntiles[1], p.ntiles[2], cnt2, tl2);
     }
-    // the last tile of a grid may be partial: its CTA takes it after the ring tiles, through guarded global accesses
+    // the last tile of a grid may be partial: its CTA takes it before the ring tiles, through guarded global accesses
     auto partial = [&](int ph, int cnt, int64_t tl) {
         return cnt > 0 && tl + (int64_t)(cnt - 1) * G == p.ntiles[ph] - 1 && (p.end[ph] - p.first[ph]) % kSpecTile != 0;
     };
@@ -576,63 +668,82 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
     const int ring0 = cnt0 - part0, ring1 = cnt1 - part1, ring2 = cnt2 - part2;      // tiles that travel through the ring
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == kSpecCW) {
+    if (warp == GEO::kWarps) {
         // ---------------- producer warp: one lane issues the bulk copies ----------------
         if (lane != 0) return;
-        {   // t tiles: group g = i mod GT covers units [g*A, g*A + A)
-            int g = 0, use = 0;
+        {   // t tiles: tile i -> stage i mod NT, barrier i mod LT
+            int st = 0, bi = 0, use = 0;          // of tile i
+            int pb = 0, puse = 0;                 // of tile i - NT, the previous tenant of the stage
             for (int i = 0; i < ring0; ++i) {
-                if (use > 0) mbar_wait(&emptyT[g], (use - 1) & 1);
+                if (i >= NT) {
+                    mbar_wait(&emptyT[pb], puse & 1);
+                    if (++pb == LT) {
+                        pb = 0;
+                        ++puse;
+                    }
+                }
                 const int64_t cell = p.first[0] + (tl0 + (int64_t)i * G) * kSpecTile;
-                mbar_expect_tx(&fullT[g], p.tx_bytes[0]);
-                char *dst = ring + (size_t)g * A * p.unit_bytes;
+                mbar_expect_tx(&fullT[bi], p.tx_bytes[0]);
+                char *dst = ring + (size_t)st * p.t_stage_bytes;
 #pragma unroll 1
-                for (int a = 0; a < kSpecMaxSlots; ++a)
-                    if (p.src[0][a]) bulk_g2s(dst + a * kSpecSlotBytes, p.src[0][a] + cell, kSpecSlotBytes, &fullT[g]);
-                if (++g == GT) {
-                    g = 0;
+                for (int a = 0; a < Lay<SET, NS>::NT; ++a)
+                    if (p.src[0][a]) bulk_g2s(dst + a * kSpecSlotBytes, p.src[0][a] + cell, kSpecSlotBytes, &fullT[bi]);
+                if (++st == NT) st = 0;
+                if (++bi == LT) {
+                    bi = 0;
                     ++use;
                 }
             }
         }
-        {   // u then v tiles: one unit each, k counts across both grids
-            int h = 0, use = 0;
+        {   // u then v tiles: tile k (counted across both grids) -> stage k mod NUS of the u/v carving, barrier k mod LU
+            int st = 0, bi = 0, k = 0;
+            int pb = 0, puse = 0;
 #pragma unroll 1
             for (int ph = 1; ph < 3; ++ph) {
                 const int cnt_ph = ph == 1 ? ring1 : ring2;
                 const int64_t tl_ph = ph == 1 ? tl1 : tl2;
-                for (int i = 0; i < cnt_ph; ++i) {
-                    if (use > 0) {
-                        mbar_wait(&emptyU[h], (use - 1) & 1);
-                    } else {      // first use of this unit: the last t tile of the group that covered it must be done
-                        const int g = h / A;
-                        const int uses_t = (ring0 > g) ? (ring0 - g + GT - 1) / GT : 0;
-                        if (uses_t > 0) mbar_wait(&emptyT[g], (uses_t - 1) & 1);
+                for (int i = 0; i < cnt_ph; ++i, ++k) {
+                    if (k >= NUS) {
+                        mbar_wait(&emptyU[pb], puse & 1);
+                        if (++pb == LU) {
+                            pb = 0;
+                            ++puse;
+                        }
+                    } else {      // first use of these bytes as a u/v stage: the last t tile of every t stage they overlap must be done
+                        const int lo = (st * p.u_stage_bytes) / p.t_stage_bytes, hi = ((st + 1) * p.u_stage_bytes - 1) / p.t_stage_bytes;
+                        for (int s = lo; s <= hi && s < NT; ++s)
+                            if (ring0 > s) {
+                                const int last = s + ((ring0 - 1 - s) / NT) * NT;      // last t tile that lived in stage s
+                                mbar_wait(&emptyT[last % LT], (last / LT) & 1);
+                            }
                     }
                     const int64_t cell = p.first[ph] + (tl_ph + (int64_t)i * G) * kSpecTile;
-                    mbar_expect_tx(&fullU[h], p.tx_bytes[ph]);
-                    char *dst = ring + (size_t)h * p.unit_bytes;
+                    mbar_expect_tx(&fullU[bi], p.tx_bytes[ph]);
+                    char *dst = ring + (size_t)st * p.u_stage_bytes;
 #pragma unroll 1
-                    for (int a = 0; a < (SET == SET_BULK ? (int)bulk::NUV : (int)rco::NUV); ++a)
-                        if (p.src[ph][a]) bulk_g2s(dst + a * kSpecSlotBytes, p.src[ph][a] + cell, kSpecSlotBytes, &fullU[h]);
-                    if (++h == NU) {
-                        h = 0;
-                        ++use;
-                    }
+                    for (int a = 0; a < Lay<SET, NS>::NUV; ++a)
+                        if (p.src[ph][a]) bulk_g2s(dst + a * kSpecSlotBytes, p.src[ph][a] + cell, kSpecSlotBytes, &fullU[bi]);
+                    if (++st == NUS) st = 0;
+                    if (++bi == LU) bi = 0;
                 }
             }
         }
         return;
     }
 
-    // ---------------- consumer warps ----------------
-    const int toff = threadIdx.x * (kSpecV * 8);
+    // ---------------- consumer warps: team = warp / 8 takes ring tiles team, team + TEAMS, ... ----------------
+    const int team = (TEAMS == 1) ? 0 : warp / kTeamWarps;
+    const int ttid = threadIdx.x - team * kTeamThreads;
+    const int toff = ttid * (kSpecV * 8);
+    const int64_t jstride = (int64_t)G * kSpecTile;
     {   // t phase
-        DiagAcc<DIAG, 6, DQ_QSUR_T> dg;
+        DiagAcc<NS, DIAG, 6, DQ_QSUR_T> dg;
         dg.reset();
-        const int64_t j0 = p.first[0] + tl0 * kSpecTile + threadIdx.x * kSpecV, jstride = (int64_t)G * kSpecTile;
-        if (part0) {      // the partial tile first: its (slow, guarded) global loads overlap the filling of the ring
-            const int64_t j = j0 + (int64_t)(cnt0 - 1) * jstride;
+        const int64_t jbase = p.first[0] + tl0 * kSpecTile + ttid * kSpecV;      // this thread's cells of ring tile 0
+        int64_t jpart = -1;
+        if (part0 && team == 0) {      // the partial tile first: its (slow, guarded) global loads overlap the filling of the ring
+            const int64_t j = jbase + (int64_t)(cnt0 - 1) * jstride;
+            jpart = j;
             const int64_t left = p.end[0] - j;
             const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
             if (DIAG) {
@@ -642,61 +753,73 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
             FastVec<kSpecV> m;
             const LdPairGuard ld{p.src[0], j, nv};
             const StPairGuard st{j, nv};
-            DiagAccGuard<DIAG, 6, DQ_QSUR_T> dgg{dg, nv};
-            spec_t_chain<SET>(m, p, ld, st, dgg);
+            DiagAccGuard<NS, DIAG, 6, DQ_QSUR_T> dgg{dg, nv};
+            spec_t_chain<SET, NS>(m, p, ld, st, dgg);
             if (__any_sync(0xffffffffu, nv > 0 && m.bad()) && lane == 0) {
                 const int n = nflagged[warp];
-                if (n < kSpecBadCap) flagged[warp][n] = cnt0 - 1;
+                if (n < kSpecBadCap) flagged[warp][n] = -1;
                 nflagged[warp] = n + 1;
             }
         }
-        int g = 0, use = 0;
-        int64_t j = j0;
-        for (int i = 0; i < ring0; ++i, j += jstride) {
+        int s = team % NT, bi = team % LT, use = team / LT, mine = 0;
+        int64_t j = jbase + (int64_t)team * jstride;
+        for (int i = team; i < ring0; i += TEAMS, j += TEAMS * jstride, ++mine) {
             if (DIAG) {
                 const double2 a = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
                 dg.area.v[0] = a.x;
                 dg.area.v[1] = a.y;
             }
-            mbar_wait(&fullT[g], use & 1);
+            mbar_wait(&fullT[bi], use & 1);
             FastVec<kSpecV> m;
-            const LdStage ld{ring + (size_t)g * A * p.unit_bytes + toff};
+            const LdStage ld{ring + (size_t)s * p.t_stage_bytes + toff};
             const StPair st{j};
-            spec_t_chain<SET>(m, p, ld, st, dg);
+            spec_t_chain<SET, NS>(m, p, ld, st, dg);
             __syncwarp();
-            if (lane == 0) mbar_arrive(&emptyT[g]);
+            if (lane == 0) mbar_arrive(&emptyT[bi]);
             if (__any_sync(0xffffffffu, m.bad()) && lane == 0) {
                 const int n = nflagged[warp];
-                if (n < kSpecBadCap) flagged[warp][n] = i;
+                if (n < kSpecBadCap) flagged[warp][n] = mine;
                 nflagged[warp] = n + 1;
             }
-            if (++g == GT) {
-                g = 0;
+            s += TEAMS;
+            while (s >= NT) s -= NT;
+            bi += TEAMS;
+            while (bi >= LT) {
+                bi -= LT;
                 ++use;
             }
         }
         __syncwarp();
         const int nf = nflagged[warp];
         if (nf) {
-            spec_cold_phase<SET, DIAG>(p, 0, j0, jstride, cnt0, flagged[warp], nf, ws);
+            spec_cold_phase<SET, NS, DIAG>(p, 0, jpart, jbase + (int64_t)team * jstride, TEAMS * jstride, mine, flagged[warp], nf, ws);
             __syncwarp();
             if (lane == 0) nflagged[warp] = 0;
+            __syncwarp();
         } else if (DIAG) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) diag_flush_one<DIAG>(ws, DQ_QSUR_T + q, dg.s[q], DIAG >= 2 ? dg.mn[q] : 0.0, DIAG >= 2 ? dg.mx[q] : 0.0);
+            for (int ty = (NS == 1 ? 1 : 0); ty <= NS; ++ty)
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int k = DiagAcc<NS, DIAG, 6, DQ_QSUR_T>::idx(ty, q);
+                    diag_flush_one<NS, DIAG>(ws, ws_index<NS>(ty, DQ_QSUR_T + q), dg.s[k], DIAG >= 2 ? dg.mn[DIAG >= 2 ? k : 0] : 0.0,
+                                             DIAG >= 2 ? dg.mx[DIAG >= 2 ? k : 0] : 0.0);
+                }
         }
     }
-    {   // u phase, then v phase: same code, same ring
-        int h = 0, use = 0;
+    {   // u phase, then v phase: same code, same carving, tile counter k runs across both grids
+        int kbase = 0;      // ring tiles of this CTA before the current grid
 #pragma unroll 1
         for (int ph = 1; ph < 3; ++ph) {
-            DiagAcc<DIAG, 2, DQ_QSUR_U> dg;
+            DiagAcc<NS, DIAG, 2, DQ_QSUR_U> dg;
             dg.reset();
             const int north = ph - 1;
             const int cnt_ph = ph == 1 ? cnt1 : cnt2, ring_ph = ph == 1 ? ring1 : ring2;
-            const int64_t j0 = p.first[ph] + (ph == 1 ? tl1 : tl2) * kSpecTile + threadIdx.x * kSpecV, jstride = (int64_t)G * kSpecTile;
-            if (ring_ph != cnt_ph) {      // partial tile of this grid, before its ring tiles
-                const int64_t j = j0 + (int64_t)(cnt_ph - 1) * jstride;
+            const int64_t jbase = p.first[ph] + (ph == 1 ? tl1 : tl2) * kSpecTile + ttid * kSpecV;
+            int64_t jpart = -1;
+            if (ring_ph != cnt_ph && team == 0) {      // partial tile of this grid, before its ring tiles
+                const int64_t j = jbase + (int64_t)(cnt_ph - 1) * jstride;
+                jpart = j;
                 const int64_t left = p.end[ph] - j;
                 const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
                 if (DIAG) {
@@ -706,53 +829,67 @@ __global__ void __launch_bounds__(kSpecThreads, 2) flux_spec_kernel(const __grid
                 FastVec<kSpecV> m;
                 const LdPairGuard ld{p.src[ph], j, nv};
                 const StPairGuard st{j, nv};
-                DiagAccGuard<DIAG, 2, DQ_QSUR_U> dgg{dg, nv};
-                spec_uv_chain<SET>(m, p, north, ld, st, dgg);
+                DiagAccGuard<NS, DIAG, 2, DQ_QSUR_U> dgg{dg, nv};
+                spec_uv_chain<SET, NS>(m, p, north, ld, st, dgg);
                 if (__any_sync(0xffffffffu, nv > 0 && m.bad()) && lane == 0) {
                     const int n = nflagged[warp];
-                    if (n < kSpecBadCap) flagged[warp][n] = cnt_ph - 1;
+                    if (n < kSpecBadCap) flagged[warp][n] = -1;
                     nflagged[warp] = n + 1;
                 }
             }
-            int64_t j = j0;
-            for (int i = 0; i < ring_ph; ++i, j += jstride) {
+            // this team's first tile of the grid: the smallest i >= 0 with (kbase + i) mod TEAMS == team
+            const int i0 = (TEAMS == 1) ? 0 : ((team - kbase) % TEAMS + TEAMS) % TEAMS;
+            int h = (kbase + i0) % NUS, bi = (kbase + i0) % LU, use = (kbase + i0) / LU, mine = 0;
+            const int64_t jfirst = jbase + (int64_t)i0 * jstride;
+            int64_t j = jfirst;
+            for (int i = i0; i < ring_ph; i += TEAMS, j += TEAMS * jstride, ++mine) {
                 if (DIAG) {
                     const double2 a = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
                     dg.area.v[0] = a.x;
                     dg.area.v[1] = a.y;
                 }
-                mbar_wait(&fullU[h], use & 1);
+                mbar_wait(&fullU[bi], use & 1);
                 FastVec<kSpecV> m;
-                const LdStage ld{ring + (size_t)h * p.unit_bytes + toff};
+                const LdStage ld{ring + (size_t)h * p.u_stage_bytes + toff};
                 const StPair st{j};
-                spec_uv_chain<SET>(m, p, north, ld, st, dg);
+                spec_uv_chain<SET, NS>(m, p, north, ld, st, dg);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyU[h]);
+                if (lane == 0) mbar_arrive(&emptyU[bi]);
                 if (__any_sync(0xffffffffu, m.bad()) && lane == 0) {
                     const int n = nflagged[warp];
-                    if (n < kSpecBadCap) flagged[warp][n] = i;
+                    if (n < kSpecBadCap) flagged[warp][n] = mine;
                     nflagged[warp] = n + 1;
                 }
-                if (++h == NU) {
-                    h = 0;
+                h += TEAMS;
+                while (h >= NUS) h -= NUS;
+                bi += TEAMS;
+                while (bi >= LU) {
+                    bi -= LU;
                     ++use;
                 }
             }
+            kbase += ring_ph;
             __syncwarp();
             const int nf = nflagged[warp];
             if (nf) {
-                spec_cold_phase<SET, DIAG>(p, ph, j0, jstride, cnt_ph, flagged[warp], nf, ws);
+                spec_cold_phase<SET, NS, DIAG>(p, ph, jpart, jfirst, TEAMS * jstride, mine, flagged[warp], nf, ws);
                 __syncwarp();
                 if (lane == 0) nflagged[warp] = 0;
                 __syncwarp();
             } else if (DIAG) {
                 const int q0 = north ? DQ_QSUR_V : DQ_QSUR_U;
-                diag_flush_one<DIAG>(ws, q0, dg.s[0], DIAG >= 2 ? dg.mn[0] : 0.0, DIAG >= 2 ? dg.mx[0] : 0.0);
-                diag_flush_one<DIAG>(ws, q0 + 1, dg.s[1], DIAG >= 2 ? dg.mn[1] : 0.0, DIAG >= 2 ? dg.mx[1] : 0.0);
+#pragma unroll
+                for (int ty = (NS == 1 ? 1 : 0); ty <= NS; ++ty)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int k = DiagAcc<NS, DIAG, 2, DQ_QSUR_U>::idx(ty, DQ_QSUR_U + q);
+                        diag_flush_one<NS, DIAG>(ws, ws_index<NS>(ty, q0 + q), dg.s[k], DIAG >= 2 ? dg.mn[DIAG >= 2 ? k : 0] : 0.0,
+                                                 DIAG >= 2 ? dg.mx[DIAG >= 2 ? k : 0] : 0.0);
+                    }
             }
         }
     }
-    if (DIAG) diag_finish<DIAG>(p, ws, &is_last);
+    if (DIAG) diag_finish<NS, DIAG>(p, ws, &is_last);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -771,29 +908,133 @@ static int spec_num_sms()
 
 static bool is_bulk(int m) { return m == M_CCLM || m == M_MOM5; }
 
+template <int SET, int NS>
+static bool spec_fill(const FusedPlan &p, SpecPlan &sp)
+{
+    using L = Lay<SET, NS>;
+    const FusedT &t = p.t;
+    const FusedTType &T0 = t.ty[0];
+    const double **s = sp.src[0];
+    s[L::PSUR] = T0.psur; s[L::QATM] = T0.qatm; s[L::TATM] = T0.tatm; s[L::UATM] = T0.uatm; s[L::VATM] = T0.vatm;
+    s[L::RSDD] = t.rsdd; s[L::BIAS] = t.bias;
+    if (SET == SET_BULK) {
+        s[L::AEV] = T0.a_evap;
+        s[L::PATM] = T0.patm;
+        if (T0.a_sens == T0.a_evap) {
+            sp.ase_slot = L::AEV;
+        } else {
+            s[L::ASE] = T0.a_sens;
+            sp.ase_slot = L::ASE;
+        }
+        if (!T0.a_evap || !T0.patm || !T0.a_sens) return false;
+    }
+    if (!T0.psur || !T0.qatm || !T0.tatm || !T0.uatm || !T0.vatm) return false;
+    bool any_avg_t = false, any_avg_uv[2] = {false, false};
+    for (int q = DQ_MEVA; q <= DQ_RSDR; ++q) any_avg_t = any_avg_t || sp.out[0][q] != nullptr;
+    sp.any_avg_t = any_avg_t;
+    any_avg_uv[0] = sp.out[0][DQ_UMOM] != nullptr;
+    any_avg_uv[1] = sp.out[0][DQ_VMOM] != nullptr;
+    for (int i = 0; i < NS; ++i) {
+        const FusedTType &T = t.ty[i];
+        // the atmosphere / shared bottom fields must be the SAME arrays for every surface type (basic.F90:334-358)
+        if (T.psur != T0.psur || T.qatm != T0.qatm || T.tatm != T0.tatm || T.uatm != T0.uatm || T.vatm != T0.vatm) return false;
+        if (SET == SET_BULK && (T.a_evap != T0.a_evap || T.a_sens != T0.a_sens || T.patm != T0.patm)) return false;
+        s[L::FICE(i)] = T.fice;
+        s[L::TSUR(i)] = T.tsur;
+        if (!T.fice || !T.tsur) return false;
+        if (NS > 1 && any_avg_t) {
+            s[L::FARE(i)] = T.fare;
+            if (!T.fare) return false;
+        }
+    }
+    for (int g = 0; g < 2; ++g) {
+        const FusedUVType &Y0 = p.uv[g].ty[0];
+        const double **u = sp.src[g + 1];
+        u[L::U_UATM] = Y0.uatm;
+        u[L::U_VATM] = Y0.vatm;
+        if (!Y0.uatm || !Y0.vatm) return false;
+        if (SET == SET_BULK) {
+            u[L::U_PSUR] = Y0.psur;
+            u[L::U_AMOM] = Y0.a_mom;
+            if (!Y0.psur || !Y0.a_mom) return false;
+        }
+        for (int i = 0; i < NS; ++i) {
+            const FusedUVType &Y = p.uv[g].ty[i];
+            if (Y.uatm != Y0.uatm || Y.vatm != Y0.vatm) return false;
+            if (SET == SET_BULK) {
+                if (Y.psur != Y0.psur || Y.a_mom != Y0.a_mom) return false;
+                u[L::U_FICE(i)] = Y.fice;
+                u[L::U_TSUR(i)] = Y.tsur;
+                if (!Y.fice || !Y.tsur) return false;
+            }
+            if (NS > 1 && any_avg_uv[g]) {
+                u[L::U_FARE(i)] = Y.fare;
+                if (!Y.fare) return false;
+            }
+        }
+    }
+    // the two carvings of the ring: as many stages as fit (2 CTAs per SM with one type, the whole SM with two)
+    int t_slots = 0, u_slots = 0;
+    for (int a = 0; a < L::NT; ++a)
+        if (sp.src[0][a]) t_slots = a + 1;
+    for (int g = 1; g < 3; ++g)
+        for (int a = 0; a < L::NUV; ++a)
+            if (sp.src[g][a]) u_slots = (a + 1 > u_slots) ? a + 1 : u_slots;
+    // 227 KB per SM, 1 KB reserved per CTA, ~3-6 KB static (barriers, flag lists, diagnostics staging)
+    const int budget = (NS == 1) ? 110 * 1024 : 220 * 1024;
+    sp.t_stage_bytes = t_slots * kSpecSlotBytes;
+    sp.u_stage_bytes = u_slots * kSpecSlotBytes;
+    sp.t_stages = budget / sp.t_stage_bytes;
+    sp.u_stages = budget / sp.u_stage_bytes;
+    if (sp.t_stages > kSpecMaxStages) sp.t_stages = kSpecMaxStages;
+    if (sp.u_stages > kSpecMaxStages) sp.u_stages = kSpecMaxStages;
+    auto lcm = [](int a, int b) {
+        int x = a, y = b;
+        while (y) {
+            const int t = x % y;
+            x = y;
+            y = t;
+        }
+        return a / x * b;
+    };
+    const int teams = (NS == 1) ? 1 : 2;
+    sp.t_bars = lcm(teams, sp.t_stages);
+    sp.u_bars = lcm(teams, sp.u_stages);
+    return sp.t_stages >= 2 && sp.u_stages >= 2 && sp.t_bars <= kSpecMaxBars && sp.u_bars <= kSpecMaxBars;
+}
+
 // cells[g] cells starting at first[g] (every bound array 16-byte aligned there: decided by the caller)
 static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t cells[3], SpecPlan &sp, int *set_out)
 {
-    if (p.S != 1 || !p.do_normal) return false;
-    const FusedTType &T = p.t.ty[0];
-    const FusedUVType &U = p.uv[0].ty[0], &W = p.uv[1].ty[0];
+    if (p.S < 1 || p.S > kSpecMaxNS || !p.do_normal) return false;
     const FusedT &t = p.t;
-    if (t.avg_qsur || t.avg_meva || t.avg_hlat || t.avg_hsen || t.avg_rbbr || t.avg_rsdr) return false;
-    if (p.uv[0].avg_qsur || p.uv[0].avg_mom || p.uv[1].avg_qsur || p.uv[1].avg_mom) return false;
-    if (T.m_qsur != M_CCLM || T.qsur_in || U.qsur_in || W.qsur_in) return false;
-    if (T.m_hlat != M_WATER && T.m_hlat != M_ICE) return false;
-    if (p.do_early ? (T.m_rbbr != M_STBO) : (T.m_rbbr != M_NONE)) return false;
-    int set;
-    if (is_bulk(T.m_meva) && is_bulk(T.m_hsen) && U.m_qsur == M_CCLM && W.m_qsur == M_CCLM && is_bulk(U.m_mom) && is_bulk(W.m_mom))
-        set = SET_BULK;
-    else if (T.m_meva == M_RCO && T.m_hsen == M_RCO && U.m_qsur == M_NONE && W.m_qsur == M_NONE && U.m_mom == M_RCO && W.m_mom == M_RCO)
-        set = SET_RCO;
-    else
-        return false;
+    if (t.avg_qsur || p.uv[0].avg_qsur || p.uv[1].avg_qsur) return false;
+    if (p.S == 1 && (t.avg_meva || t.avg_hlat || t.avg_hsen || t.avg_rbbr || t.avg_rsdr || p.uv[0].avg_mom || p.uv[1].avg_mom)) return false;
+    // two surface types with diagnostics: 17 (sums) to 51 (sums + min/max) running accumulators per thread do not fit the
+    // register file next to the chain (measured: 712 bytes of spills, 1.31 ms against 0.99 ms on the direct-load kernel)
+    if (p.S > 1 && p.diag >= 1) return false;
+    int set = -1;
+    for (int i = 0; i < p.S; ++i) {
+        const FusedTType &T = t.ty[i];
+        const FusedUVType &U = p.uv[0].ty[i], &W = p.uv[1].ty[i];
+        if (T.m_qsur != M_CCLM || T.qsur_in || U.qsur_in || W.qsur_in) return false;
+        if (T.m_hlat != M_WATER && T.m_hlat != M_ICE) return false;
+        if (p.do_early ? (T.m_rbbr != M_STBO) : (T.m_rbbr != M_NONE)) return false;
+        int si;
+        if (is_bulk(T.m_meva) && is_bulk(T.m_hsen) && U.m_qsur == M_CCLM && W.m_qsur == M_CCLM && is_bulk(U.m_mom) && is_bulk(W.m_mom))
+            si = SET_BULK;
+        else if (T.m_meva == M_RCO && T.m_hsen == M_RCO && U.m_qsur == M_NONE && W.m_qsur == M_NONE && U.m_mom == M_RCO && W.m_mom == M_RCO)
+            si = SET_RCO;
+        else
+            return false;
+        if (set >= 0 && si != set) return false;
+        set = si;
+    }
     if (p.diag && !(t.area && p.uv[0].area && p.uv[1].area)) return false;
 
     memset(&sp, 0, sizeof sp);
     sp.c = p.c;
+    sp.ns = p.S;
     for (int g = 0; g < 3; ++g) {
         sp.first[g] = first[g];
         sp.end[g] = first[g] + cells[g];
@@ -802,46 +1043,31 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     sp.do_early = p.do_early;
     sp.has_bias = t.bias != nullptr;
     sp.has_rsdr = t.rsdd != nullptr;
-    sp.latent_heat = T.latent_heat;
     sp.diag = p.diag;
-    if (set == SET_BULK) {
-        const double **s = sp.src[0];
-        s[bulk::FICE] = T.fice; s[bulk::PSUR] = T.psur; s[bulk::TSUR] = T.tsur; s[bulk::QATM] = T.qatm; s[bulk::TATM] = T.tatm;
-        s[bulk::UATM] = T.uatm; s[bulk::VATM] = T.vatm; s[bulk::AEV] = T.a_evap; s[bulk::PATM] = T.patm;
-        s[bulk::RSDD] = t.rsdd; s[bulk::BIAS] = t.bias;
-        if (T.a_sens == T.a_evap) {
-            sp.ase_slot = bulk::AEV;
-        } else {
-            s[bulk::ASE] = T.a_sens;
-            sp.ase_slot = bulk::ASE;
-        }
-        for (int k = 0; k <= bulk::PATM; ++k)
-            if (!s[k]) return false;
-        for (int g = 0; g < 2; ++g) {
-            const FusedUVType &Y = p.uv[g].ty[0];
-            const double **u = sp.src[g + 1];
-            u[bulk::U_FICE] = Y.fice; u[bulk::U_PSUR] = Y.psur; u[bulk::U_TSUR] = Y.tsur; u[bulk::U_UATM] = Y.uatm;
-            u[bulk::U_VATM] = Y.vatm; u[bulk::U_AMOM] = Y.a_mom;
-            for (int k = 0; k < bulk::NUV; ++k)
-                if (!u[k]) return false;
-        }
-        sp.t_units = bulk::kTUnits;
-        sp.unit_bytes = bulk::kUnitSlots * kSpecSlotBytes;
-    } else {
-        const double **s = sp.src[0];
-        s[rco::FICE] = T.fice; s[rco::PSUR] = T.psur; s[rco::TSUR] = T.tsur; s[rco::QATM] = T.qatm; s[rco::TATM] = T.tatm;
-        s[rco::UATM] = T.uatm; s[rco::VATM] = T.vatm; s[rco::RSDD] = t.rsdd; s[rco::BIAS] = t.bias;
-        for (int k = 0; k <= rco::VATM; ++k)
-            if (!s[k]) return false;
-        for (int g = 0; g < 2; ++g) {
-            const FusedUVType &Y = p.uv[g].ty[0];
-            sp.src[g + 1][rco::U_UATM] = Y.uatm;
-            sp.src[g + 1][rco::U_VATM] = Y.vatm;
-            if (!Y.uatm || !Y.vatm) return false;
-        }
-        sp.t_units = rco::kTUnits;
-        sp.unit_bytes = rco::kUnitSlots * kSpecSlotBytes;
+    for (int i = 0; i < p.S; ++i) {
+        const FusedTType &T = t.ty[i];
+        const FusedUVType &U = p.uv[0].ty[i], &W = p.uv[1].ty[i];
+        double **o = sp.out[i + 1];
+        sp.latent_heat[i] = T.latent_heat;
+        o[DQ_QSUR_T] = T.qsur; o[DQ_MEVA] = T.meva; o[DQ_HLAT] = T.hlat; o[DQ_HSEN] = T.hsen;
+        o[DQ_RBBR] = p.do_early ? T.rbbr : nullptr;
+        o[DQ_RSDR] = sp.has_rsdr ? T.rsdr : nullptr;
+        o[DQ_QSUR_U] = U.qsur; o[DQ_UMOM] = U.mom; o[DQ_QSUR_V] = W.qsur; o[DQ_VMOM] = W.mom;
+        if (!T.qsur || !T.meva || !T.hlat || !T.hsen || !U.mom || !W.mom) return false;
+        if (set == SET_BULK && (!U.qsur || !W.qsur)) return false;
+        if (p.do_early && !T.rbbr) return false;
+        if (sp.has_rsdr && !T.rsdr) return false;
     }
+    sp.out[0][DQ_MEVA] = t.avg_meva; sp.out[0][DQ_HLAT] = t.avg_hlat; sp.out[0][DQ_HSEN] = t.avg_hsen;
+    sp.out[0][DQ_RBBR] = p.do_early ? t.avg_rbbr : nullptr;
+    sp.out[0][DQ_RSDR] = sp.has_rsdr ? t.avg_rsdr : nullptr;
+    sp.out[0][DQ_UMOM] = p.uv[0].avg_mom;
+    sp.out[0][DQ_VMOM] = p.uv[1].avg_mom;
+    if (!p.do_early && t.avg_rbbr) return false;
+    bool ok;
+    if (set == SET_BULK) ok = (p.S == 1) ? spec_fill<SET_BULK, 1>(p, sp) : spec_fill<SET_BULK, 2>(p, sp);
+    else ok = (p.S == 1) ? spec_fill<SET_RCO, 1>(p, sp) : spec_fill<SET_RCO, 2>(p, sp);
+    if (!ok) return false;
     for (int g = 0; g < 3; ++g) {
         int n = 0;
         for (int k = 0; k < kSpecMaxSlots; ++k) n += sp.src[g][k] != nullptr;
@@ -850,22 +1076,7 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     sp.area[0] = t.area;
     sp.area[1] = p.uv[0].area;
     sp.area[2] = p.uv[1].area;
-    sp.outq[DQ_QSUR_T] = T.qsur; sp.outq[DQ_MEVA] = T.meva; sp.outq[DQ_HLAT] = T.hlat; sp.outq[DQ_HSEN] = T.hsen;
-    sp.outq[DQ_RBBR] = p.do_early ? T.rbbr : nullptr;
-    sp.outq[DQ_RSDR] = sp.has_rsdr ? T.rsdr : nullptr;
-    sp.outq[DQ_QSUR_U] = U.qsur; sp.outq[DQ_UMOM] = U.mom; sp.outq[DQ_QSUR_V] = W.qsur; sp.outq[DQ_VMOM] = W.mom;
-    if (!T.qsur || !T.meva || !T.hlat || !T.hsen || !U.mom || !W.mom) return false;
-    if (set == SET_BULK && (!U.qsur || !W.qsur)) return false;
-    if (p.do_early && !T.rbbr) return false;
-    if (sp.has_rsdr && !T.rsdr) return false;
-    // ring: as many units as fit next to a second CTA on the SM (227 KB - 1 KB reserved per CTA - static), a multiple of t_units
-    const int budget = 112 * 1024;
-    int units = budget / sp.unit_bytes;
-    if (units > kSpecMaxUnits) units = kSpecMaxUnits;
-    units -= units % sp.t_units;
-    if (units < 2 * sp.t_units) return false;
-    sp.units = units;
-    for (int q = 0; q < DQ_COUNT; ++q) sp.dmap[q] = p.diag ? p.diag_map[DQ_COUNT + q] : (signed char)-1;    // surface type 1
+    for (int k = 0; k < (kSpecMaxNS + 1) * DQ_COUNT; ++k) sp.dmap[k] = p.diag ? p.diag_map[k] : (signed char)-1;
     sp.partials = p.diag_partials;
     sp.rows = p.diag_rows;
     sp.plane = (int64_t)p.diag_n * p.diag_rows;
@@ -880,7 +1091,7 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
 static int spec_grid(const SpecPlan &sp)
 {
     const int64_t total = (int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2];
-    const int cap = 2 * spec_num_sms();
+    const int cap = (sp.ns == 1 ? 2 : 1) * spec_num_sms();
     return (int)(total < cap ? total : cap);
 }
 
@@ -893,15 +1104,16 @@ int spec_applicable(const FusedPlan &p, const int64_t first[3], const int64_t ce
     return spec_grid(sp);
 }
 
-template <int SET, int DIAG>
+template <int SET, int NS, int DIAG>
 static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stream)
 {
-    const size_t smem = (size_t)sp.units * sp.unit_bytes;
+    const size_t tb = (size_t)sp.t_stages * sp.t_stage_bytes, ub = (size_t)sp.u_stages * sp.u_stage_bytes;
+    const size_t smem = tb > ub ? tb : ub;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(flux_spec_kernel<SET, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(flux_spec_kernel<SET, NS, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(flux_spec_kernel<SET, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(flux_spec_kernel<SET, NS, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -909,7 +1121,7 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
     // drains; the kernel itself waits (griddepcontrol.wait) before its first global access
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kSpecThreads);
+    cfg.blockDim = dim3(SpecGeom<NS>::kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -917,7 +1129,21 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, flux_spec_kernel<SET, DIAG>, sp);
+    return cudaLaunchKernelEx(&cfg, flux_spec_kernel<SET, NS, DIAG>, sp);
+}
+
+template <int SET, int NS>
+static cudaError_t spec_launch_d(const SpecPlan &sp, int grid, cudaStream_t stream)
+{
+    if (sp.diag >= 2) {
+        if constexpr (NS == 1) return spec_launch_t<SET, NS, 2>(sp, grid, stream);
+        else return cudaErrorInvalidValue;      // spec_build refuses this combination
+    }
+    if (sp.diag == 1) {
+        if constexpr (NS == 1) return spec_launch_t<SET, NS, 1>(sp, grid, stream);
+        else return cudaErrorInvalidValue;
+    }
+    return spec_launch_t<SET, NS, 0>(sp, grid, stream);
 }
 
 int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[3], cudaStream_t stream)
@@ -928,15 +1154,8 @@ int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[
     if (sp.diag && (!sp.partials || !sp.diag_out || !sp.counter)) return (int)cudaErrorInvalidValue;
     const int grid = spec_grid(sp);
     cudaError_t e;
-    if (set == SET_BULK) {
-        if (sp.diag >= 2) e = spec_launch_t<SET_BULK, 2>(sp, grid, stream);
-        else if (sp.diag == 1) e = spec_launch_t<SET_BULK, 1>(sp, grid, stream);
-        else e = spec_launch_t<SET_BULK, 0>(sp, grid, stream);
-    } else {
-        if (sp.diag >= 2) e = spec_launch_t<SET_RCO, 2>(sp, grid, stream);
-        else if (sp.diag == 1) e = spec_launch_t<SET_RCO, 1>(sp, grid, stream);
-        else e = spec_launch_t<SET_RCO, 0>(sp, grid, stream);
-    }
+    if (set == SET_BULK) e = (sp.ns == 1) ? spec_launch_d<SET_BULK, 1>(sp, grid, stream) : spec_launch_d<SET_BULK, 2>(sp, grid, stream);
+    else e = (sp.ns == 1) ? spec_launch_d<SET_RCO, 1>(sp, grid, stream) : spec_launch_d<SET_RCO, 2>(sp, grid, stream);
     return (int)e;
 }
 

@@ -303,3 +303,33 @@ def test_chunked_host_pipeline_with_diagnostics(fcmod, S, staged):
         if g1[k].size:
             d1, d7 = fc1.diagnostics(*k), fc7.diagnostics(*k)
             assert d1[1:] == d7[1:] and abs(d1[0] - d7[0]) <= 1e-12 * abs(d1[0]) + 1e-300, k
+
+
+@pytest.mark.parametrize("fset", ["CCLM", "MOM5", "RCO"])
+@pytest.mark.parametrize("level", [0, 1])
+def test_spec_kernel_two_surface_types_long_schedule(fcmod, fset, level):
+    """two surface types: one CTA per SM, two consumer teams sharing the ring (one barrier per (team, stage) pair);
+    several tiles per team and per stage so that the barrier phases wrap, ragged remainders, averaging of the sent
+    fluxes; bitwise equal to the direct-load kernel, within tolerance of the oracle"""
+    from components.flux_calculator_b200.synthetic import Scenario
+    n = (512 * 148 * 9 + 300, 512 * 148 * 5 + 1, 512 * 148 * 6 + 511)
+    sc = Scenario(fset, n=n, S=2, bias=True, averaging=True)
+    _, o_out, d_out, _, _ = run_both(fcmod, sc, "device", staged=0, diagnostics=level)
+    fc, _, s_out, _, _ = run_both(fcmod, sc, "device", staged=2, diagnostics=level)
+    assert fc.info("spec_kernel") == (1 if level == 0 else 0)      # with diagnostics two types stay on the direct-load kernel
+    compare(sc, o_out, s_out)
+    if level:
+        _diag_check(fc, sc, s_out, level)
+    for k in d_out:
+        assert np.array_equal(d_out[k], s_out[k], equal_nan=True), k
+
+
+def test_spec_kernel_two_surface_types_without_averaging(fcmod):
+    from components.flux_calculator_b200.synthetic import Scenario
+    sc = Scenario("CCLM", n=(200000, 100001, 99999), S=2, bias=True, averaging=False)
+    _, o_out, d_out, _, _ = run_both(fcmod, sc, "device", staged=0)
+    fc, _, s_out, _, _ = run_both(fcmod, sc, "device", staged=2)
+    assert fc.info("spec_kernel") == 1
+    compare(sc, o_out, s_out)
+    for k in d_out:
+        assert np.array_equal(d_out[k], s_out[k], equal_nan=True), k
