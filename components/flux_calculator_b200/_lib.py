@@ -89,6 +89,11 @@ SIGNATURES = {
     "fc_get_diagnostics": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_double_p]),
     "fc_comm_get_unique_id": (C.c_int, [C.c_char_p]),
     "fc_comm_init": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_int]),
+    "fc_configure_from_namelist": (C.c_int, [ctx_p, C.c_char_p, C.c_int]),
+    "fc_load_corrections": (C.c_int, [ctx_p, C.c_char_p, i64, C.c_int]),
+    "fc_last_warning": (C.c_char_p, [ctx_p]),
+    "fc_namelist_get": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, c_int64_p, C.c_int, c_int64_p, C.c_char_p, C.c_int]),
+    "fc_nc_read_var_double": (C.c_int, [C.c_char_p, C.c_char_p, i64, i64, c_double_p, c_double_p, C.POINTER(C.c_int)]),
     "fc_comm_p2p_handle": (C.c_int, [ctx_p, C.c_char_p]),
     "fc_comm_p2p_connect": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_int]),
     "fc_allreduce_diagnostics": (C.c_int, [ctx_p]),

@@ -150,6 +150,11 @@ struct fc_context {
     size_t prof_used = 0;
     cudaEvent_t user_ev[2] = {nullptr, nullptr};
 
+    // front end (frontend.cu): &correctionsctl of the last namelist read, warnings of the corrections loader
+    bool nml_read = false;
+    bool nml_lcorrections = false;
+    std::string warning;
+
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // of the last step call
     std::string err;

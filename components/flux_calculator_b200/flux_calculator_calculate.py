@@ -191,6 +191,16 @@ class FluxCalculator:
     def allreduce_diagnostics(self):
         self._check(lib.fc_allreduce_diagnostics(self._ctx))
 
+    # ---- the reference's configuration files ("next" rows 3-4) ---------------------------------
+    def configure_from_namelist(self, nml_path, bottom_model=1):
+        """&input which_* and &correctionsctl of a flux_calculator.nml (flux_calculator.F90:99-130, bias_corrections.F90:60-76)"""
+        self._check(lib.fc_configure_from_namelist(self._ctx, str(nml_path).encode(), int(bottom_model)))
+
+    def load_corrections(self, root_dir, grid_offset=0, reference_start_quirk=False):
+        """initialize_bias_corrections (bias_corrections.F90:165-249); returns the loader's warnings"""
+        self._check(lib.fc_load_corrections(self._ctx, str(root_dir).encode(), int(grid_offset), int(bool(reference_start_quirk))))
+        return lib.fc_last_warning(self._ctx).decode()
+
     # ---- regridding ("next" row) ---------------------------------------------------------------
     def set_regrid_matrix(self, direction, src_index, dst_index, weight):
         s = np.ascontiguousarray(src_index, dtype=np.int32)
@@ -204,6 +214,30 @@ class FluxCalculator:
         dp = dst.ptr if isinstance(dst, DeviceArray) else dst.ctypes.data
         sp = src.ptr if isinstance(src, DeviceArray) else src.ctypes.data
         self._check(lib.fc_regrid(self._ctx, direction, dp, sp))
+
+
+def namelist_get(nml_path, group, name, shape=(), index=()):
+    """one element of a namelist array (1-based index, declared shape) as text, None if the namelist does not set it"""
+    rank = len(shape)
+    shp = (C.c_int64 * max(rank, 1))(*shape)
+    idx = (C.c_int64 * max(rank, 1))(*index)
+    out = C.create_string_buffer(256)
+    rc = lib.fc_namelist_get(str(nml_path).encode(), group.encode(), name.encode(), shp, rank, idx, out, 256)
+    if rc == 20:
+        return None
+    check(rc)
+    return out.value.decode()
+
+
+def nc_read_var(path, varname, start, count):
+    """elements [start, start+count) of a NetCDF classic variable as float64, plus its _FillValue (or None)"""
+    out = np.empty(count, dtype=np.float64)
+    fill, has = C.c_double(), C.c_int()
+    rc = lib.fc_nc_read_var_double(str(path).encode(), varname.encode(), int(start), int(count),
+                                   out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(fill), C.byref(has))
+    if rc:
+        raise OSError(rc, lib.fc_last_error(None).decode())
+    return out, (fill.value if has.value else None)
 
 
 def comm_get_unique_id():

@@ -154,6 +154,20 @@ module fluxcalc_c_api
       character(kind=c_char), intent(in) :: id(128)
       integer(c_int), value :: rank, nranks
     end function
+    ! the reference's own configuration files ("next" rows 3-4): flux_calculator.nml and corrections/mass_evap-MM.nc
+    integer(c_int) function fc_configure_from_namelist(ctx, nml_path, bottom_model) bind(c, name='fc_configure_from_namelist')
+      import :: c_ptr, c_int, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(in) :: nml_path(*)      ! NUL-terminated
+      integer(c_int), value :: bottom_model
+    end function
+    integer(c_int) function fc_load_corrections(ctx, root_dir, grid_offset, reference_start_quirk) bind(c, name='fc_load_corrections')
+      import :: c_ptr, c_int, c_int64_t, c_char
+      type(c_ptr), value :: ctx
+      character(kind=c_char), intent(in) :: root_dir(*)      ! NUL-terminated; contains corrections/
+      integer(c_int64_t), value :: grid_offset
+      integer(c_int), value :: reference_start_quirk
+    end function
     ! peer-memory exchange fused into the step (one process per GPU on one NVLink node): export the mailbox handle,
     ! MPI_Allgather the 64-byte handles, connect; afterwards every step posts its diagnostics to all ranks
     integer(c_int) function fc_comm_p2p_handle(ctx, handle) bind(c, name='fc_comm_p2p_handle')

@@ -307,6 +307,33 @@ int fc_set_regrid_matrix(fc_context *ctx, int direction, int64_t num_elements, c
 /* dst(1:n_dst) = M * src for one array pair (host or device pointers) */
 int fc_regrid(fc_context *ctx, int direction, double *dst, const double *src);
 
+/* ------------------------------------------------------------------------------------------------
+ * "Next" rows 3-4: the reference's own configuration files (host code, frontend.cu)
+ * ---------------------------------------------------------------------------------------------- */
+/* Reads the method selection of bottom model `bottom_model` (1-based first index of the which_* arrays,
+ * flux_calculator.F90:99-107, NAMELIST /input/ :109-130) for surface types 1..S from a flux_calculator.nml and applies
+ * it with fc_set_method (unset entries keep the declared default 'none'); reads &correctionsctl init_date and
+ * lcorrections(1) (bias_corrections.F90:60-76) for fc_load_corrections.  Standard Fortran namelist input: comments,
+ * r*c repeats, null values, element / section subscripts, array element order. */
+int fc_configure_from_namelist(fc_context *ctx, const char *nml_path, int bottom_model);
+/* initialize_bias_corrections (bias_corrections.F90:165-249): if lcorrections is set, reads variable 'mass_evap' of
+ * <root_dir>/corrections/mass_evap-01.nc ... -12.nc (NetCDF classic CDF-1/2/5), cells [grid_offset, grid_offset + n_t),
+ * replaces _FillValue by 0 and hands the (1,12,n_t) array to fc_set_corrections.  A month whose file, variable or
+ * _FillValue attribute is missing stays zero with a line in fc_last_warning ("... Unset correction.", like the
+ * reference).  reference_start_quirk = 1 reproduces the reference's use of the 0-based offset as 1-based NetCDF start
+ * (rank 0 reads nothing, other ranks read shifted by one cell); 0 reads the intended cells. */
+int fc_load_corrections(fc_context *ctx, const char *root_dir, int64_t grid_offset, int reference_start_quirk);
+const char *fc_last_warning(const fc_context *ctx);
+/* the two parsers on their own (no device needed).  fc_namelist_get: value of element index[0..rank) (1-based) of an
+ * array declared with `shape` (rank 0: scalar) as text; returns FC_NML_UNSET if the namelist does not set it.
+ * fc_nc_read_var_double: elements [start0, start0+count) of a variable in row-major order converted to double;
+ * returns 0, or 101 cannot open, 102 not NetCDF classic, 103 no such variable, 104 range. */
+#define FC_NML_UNSET 20
+int fc_namelist_get(const char *nml_path, const char *group, const char *name, const int64_t *shape, int rank,
+                    const int64_t *index, char *out, int outlen);
+int fc_nc_read_var_double(const char *path, const char *varname, int64_t start0, int64_t count, double *out,
+                          double *fill_value, int *has_fill_value);
+
 #ifdef __cplusplus
 }
 #endif
