@@ -38,16 +38,36 @@
 namespace fc {
 
 constexpr int kSpecV = 2;
-constexpr int kTeamWarps = kFusedThreads / 32;           // consumer warps of one team: one 512-cell tile per pass
-constexpr int kTeamThreads = kTeamWarps * 32;
-constexpr int kSpecTile = kTeamThreads * kSpecV;
-constexpr int kSpecSlotBytes = kSpecTile * 8;            // one array of one tile
+// CTA geometry per number of surface types.  One type: 2 CTAs per SM, one team of 8 consumer warps, 512-cell tiles.
+// Two types (15-16 input arrays per t tile): 1 CTA per SM, two teams of 8 warps sharing three 60 KB t stages (two in
+// work, one in flight); the finer variant (four teams of 4 warps on 256-cell tiles, 7 stages of 30 KB) measured slower.
+// Tuning switches, settled by an A/B on one B200 (profiles/run18.sh, 3 repetitions each, C5 = 10^7 cells, two types):
+//   teams x producer          2 x one lane   2 x lane per slot   4 x one lane   4 x lane per slot
+//   C5 ms / step              0.852-0.861    0.892-0.905         1.054-1.058    0.898-0.906
+//   C4 ms / step (one type)   0.434-0.445    0.437               0.435-0.444    0.437
+#ifndef FC_SPEC2_TEAMS
+#define FC_SPEC2_TEAMS 2            // two surface types: 2 teams x 8 warps x 512-cell tiles, or 4 teams x 4 warps x 256-cell tiles
+#endif
+#ifndef FC_SPEC_PAR_PRODUCER
+#define FC_SPEC_PAR_PRODUCER 0      // 0: lane 0 of the producer warp issues all bulk copies of a tile; 1: lane a issues slot a
+#endif
+template <int NS>
+struct SpecGeom {
+    static constexpr int kTeams = (NS == 1) ? 1 : FC_SPEC2_TEAMS;
+    static constexpr int kTeamWarps = (NS == 1) ? 8 : 16 / FC_SPEC2_TEAMS;     // consumer warps of one team = one tile per pass
+    static constexpr int kTeamThreads = kTeamWarps * 32;
+    static constexpr int kTile = kTeamThreads * kSpecV;      // cells per tile
+    static constexpr int kSlotBytes = kTile * 8;             // one array of one tile
+    static constexpr int kConsumers = kTeams * kTeamThreads;
+    static constexpr int kThreads = kConsumers + 32;         // + producer warp
+    static constexpr int kWarps = kTeams * kTeamWarps;
+    static constexpr int kCtasPerSm = (NS == 1) ? 2 : 1;
+};
 constexpr int kSpecMaxStages = 16;
 constexpr int kSpecMaxBars = 32;                         // barriers per set: lcm(teams, stages) <= 2 * 16
 constexpr int kSpecMaxSlots = 16;
 constexpr int kSpecMaxNS = 2;                            // surface types the specialised kernel handles
 constexpr int kSpecBadCap = 16;                          // flagged tiles remembered per warp and phase; more -> all
-static_assert(kSpecTile == kFusedCellsPerBlock, "tile size is shared with the generic kernels' geometry");
 
 using S2 = Vd<kSpecV>;
 
@@ -108,7 +128,7 @@ struct SpecPlan {
 
 template <int NS, int DIAG>
 struct WarpSums {    // per-CTA staging of the consumer warps' diagnostics
-    static constexpr int kWarps = (NS == 1 ? 1 : 2) * kTeamWarps;
+    static constexpr int kWarps = SpecGeom<NS>::kWarps;
     static constexpr int kSlots = (NS == 1 ? 1 : NS + 1) * DQ_COUNT;
     double v[DIAG >= 2 ? 3 : 1][kSlots][kWarps];
 };
@@ -159,11 +179,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // operand sources, result sinks, diagnostics accumulators
 // ---------------------------------------------------------------------------------------------
 // hot path: this thread's 16 bytes of each slot of the current stage
+template <int SLOT_BYTES>
 struct LdStage {
     const char *base;
     __device__ __forceinline__ S2 operator()(int slot) const
     {
-        const double2 t = *reinterpret_cast<const double2 *>(base + slot * kSpecSlotBytes);
+        const double2 t = *reinterpret_cast<const double2 *>(base + slot * SLOT_BYTES);
         S2 r;
         r.v[0] = t.x;
         r.v[1] = t.y;
@@ -319,7 +340,7 @@ __device__ __forceinline__ void diag_flush_one(WarpSums<NS, DIAG> &ws, int wsi, 
 template <int NS>
 __device__ __forceinline__ void consumer_barrier()
 {
-    asm volatile("bar.sync 1, %0;" ::"n"((NS == 1 ? 1 : 2) * kTeamThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(SpecGeom<NS>::kConsumers) : "memory");
 }
 
 // end of kernel, consumer warps only: warps -> one row per CTA -> (last CTA) rows of all CTAs -> result (+ peer mailboxes)
@@ -592,15 +613,6 @@ __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t 
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int NS>
-struct SpecGeom {
-    static constexpr int kTeams = (NS == 1) ? 1 : 2;
-    static constexpr int kConsumers = kTeams * kTeamThreads;
-    static constexpr int kThreads = kConsumers + 32;         // + producer warp
-    static constexpr int kWarps = kTeams * kTeamWarps;
-    static constexpr int kCtasPerSm = (NS == 1) ? 2 : 1;
-};
-
 template <int SET, int NS, int DIAG>
 __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPerSm) flux_spec_kernel(const __grid_constant__ SpecPlan p)
 {
@@ -620,9 +632,9 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     if (threadIdx.x == 0) {
         for (int s = 0; s < kSpecMaxBars; ++s) {
             mbar_init(&fullT[s], 1);                // one expect_tx arrival + the bytes
-            mbar_init(&emptyT[s], kTeamWarps);      // one arrival per consumer warp of the team that took the tile
+            mbar_init(&emptyT[s], GEO::kTeamWarps);      // one arrival per consumer warp of the team that took the tile
             mbar_init(&fullU[s], 1);
-            mbar_init(&emptyU[s], kTeamWarps);
+            mbar_init(&emptyU[s], GEO::kTeamWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -662,32 +674,39 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     }
     // the last tile of a grid may be partial: its CTA takes it before the ring tiles, through guarded global accesses
     auto partial = [&](int ph, int cnt, int64_t tl) {
-        return cnt > 0 && tl + (int64_t)(cnt - 1) * G == p.ntiles[ph] - 1 && (p.end[ph] - p.first[ph]) % kSpecTile != 0;
+        return cnt > 0 && tl + (int64_t)(cnt - 1) * G == p.ntiles[ph] - 1 && (p.end[ph] - p.first[ph]) % GEO::kTile != 0;
     };
     const int part0 = partial(0, cnt0, tl0), part1 = partial(1, cnt1, tl1), part2 = partial(2, cnt2, tl2);
     const int ring0 = cnt0 - part0, ring1 = cnt1 - part1, ring2 = cnt2 - part2;      // tiles that travel through the ring
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == GEO::kWarps) {
-        // ---------------- producer warp: one lane issues the bulk copies ----------------
-        if (lane != 0) return;
+        // ---------------- producer warp: lane 0 waits, arms the barrier and issues the bulk copies ----------------
+        if (!FC_SPEC_PAR_PRODUCER && lane != 0) return;
         {   // t tiles: tile i -> stage i mod NT, barrier i mod LT
             int st = 0, bi = 0, use = 0;          // of tile i
             int pb = 0, puse = 0;                 // of tile i - NT, the previous tenant of the stage
             for (int i = 0; i < ring0; ++i) {
                 if (i >= NT) {
-                    mbar_wait(&emptyT[pb], puse & 1);
+                    if (lane == 0) mbar_wait(&emptyT[pb], puse & 1);
                     if (++pb == LT) {
                         pb = 0;
                         ++puse;
                     }
                 }
-                const int64_t cell = p.first[0] + (tl0 + (int64_t)i * G) * kSpecTile;
-                mbar_expect_tx(&fullT[bi], p.tx_bytes[0]);
+                const int64_t cell = p.first[0] + (tl0 + (int64_t)i * G) * GEO::kTile;
+                if (lane == 0) mbar_expect_tx(&fullT[bi], p.tx_bytes[0]);
+                __syncwarp();
                 char *dst = ring + (size_t)st * p.t_stage_bytes;
+                static_assert(Lay<SET, NS>::NT <= 32 && Lay<SET, NS>::NUV <= 32, "one lane per slot");
+                if (FC_SPEC_PAR_PRODUCER) {
+                    if (lane < Lay<SET, NS>::NT && p.src[0][lane])
+                        bulk_g2s(dst + lane * GEO::kSlotBytes, p.src[0][lane] + cell, GEO::kSlotBytes, &fullT[bi]);
+                } else {
 #pragma unroll 1
-                for (int a = 0; a < Lay<SET, NS>::NT; ++a)
-                    if (p.src[0][a]) bulk_g2s(dst + a * kSpecSlotBytes, p.src[0][a] + cell, kSpecSlotBytes, &fullT[bi]);
+                    for (int a = 0; a < Lay<SET, NS>::NT; ++a)
+                        if (p.src[0][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[0][a] + cell, GEO::kSlotBytes, &fullT[bi]);
+                }
                 if (++st == NT) st = 0;
                 if (++bi == LT) {
                     bi = 0;
@@ -704,12 +723,12 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
                 const int64_t tl_ph = ph == 1 ? tl1 : tl2;
                 for (int i = 0; i < cnt_ph; ++i, ++k) {
                     if (k >= NUS) {
-                        mbar_wait(&emptyU[pb], puse & 1);
+                        if (lane == 0) mbar_wait(&emptyU[pb], puse & 1);
                         if (++pb == LU) {
                             pb = 0;
                             ++puse;
                         }
-                    } else {      // first use of these bytes as a u/v stage: the last t tile of every t stage they overlap must be done
+                    } else if (lane == 0) {      // first use of these bytes as a u/v stage: the last t tile of every t stage they overlap must be done
                         const int lo = (st * p.u_stage_bytes) / p.t_stage_bytes, hi = ((st + 1) * p.u_stage_bytes - 1) / p.t_stage_bytes;
                         for (int s = lo; s <= hi && s < NT; ++s)
                             if (ring0 > s) {
@@ -717,12 +736,18 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
                                 mbar_wait(&emptyT[last % LT], (last / LT) & 1);
                             }
                     }
-                    const int64_t cell = p.first[ph] + (tl_ph + (int64_t)i * G) * kSpecTile;
-                    mbar_expect_tx(&fullU[bi], p.tx_bytes[ph]);
+                    const int64_t cell = p.first[ph] + (tl_ph + (int64_t)i * G) * GEO::kTile;
+                    if (lane == 0) mbar_expect_tx(&fullU[bi], p.tx_bytes[ph]);
+                    __syncwarp();
                     char *dst = ring + (size_t)st * p.u_stage_bytes;
+                    if (FC_SPEC_PAR_PRODUCER) {
+                        if (lane < Lay<SET, NS>::NUV && p.src[ph][lane])
+                            bulk_g2s(dst + lane * GEO::kSlotBytes, p.src[ph][lane] + cell, GEO::kSlotBytes, &fullU[bi]);
+                    } else {
 #pragma unroll 1
-                    for (int a = 0; a < Lay<SET, NS>::NUV; ++a)
-                        if (p.src[ph][a]) bulk_g2s(dst + a * kSpecSlotBytes, p.src[ph][a] + cell, kSpecSlotBytes, &fullU[bi]);
+                        for (int a = 0; a < Lay<SET, NS>::NUV; ++a)
+                            if (p.src[ph][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[ph][a] + cell, GEO::kSlotBytes, &fullU[bi]);
+                    }
                     if (++st == NUS) st = 0;
                     if (++bi == LU) bi = 0;
                 }
@@ -732,14 +757,14 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     }
 
     // ---------------- consumer warps: team = warp / 8 takes ring tiles team, team + TEAMS, ... ----------------
-    const int team = (TEAMS == 1) ? 0 : warp / kTeamWarps;
-    const int ttid = threadIdx.x - team * kTeamThreads;
+    const int team = (TEAMS == 1) ? 0 : warp / GEO::kTeamWarps;
+    const int ttid = threadIdx.x - team * GEO::kTeamThreads;
     const int toff = ttid * (kSpecV * 8);
-    const int64_t jstride = (int64_t)G * kSpecTile;
+    const int64_t jstride = (int64_t)G * GEO::kTile;
     {   // t phase
         DiagAcc<NS, DIAG, 6, DQ_QSUR_T> dg;
         dg.reset();
-        const int64_t jbase = p.first[0] + tl0 * kSpecTile + ttid * kSpecV;      // this thread's cells of ring tile 0
+        const int64_t jbase = p.first[0] + tl0 * GEO::kTile + ttid * kSpecV;      // this thread's cells of ring tile 0
         int64_t jpart = -1;
         if (part0 && team == 0) {      // the partial tile first: its (slow, guarded) global loads overlap the filling of the ring
             const int64_t j = jbase + (int64_t)(cnt0 - 1) * jstride;
@@ -771,7 +796,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
             }
             mbar_wait(&fullT[bi], use & 1);
             FastVec<kSpecV> m;
-            const LdStage ld{ring + (size_t)s * p.t_stage_bytes + toff};
+            const LdStage<GEO::kSlotBytes> ld{ring + (size_t)s * p.t_stage_bytes + toff};
             const StPair st{j};
             spec_t_chain<SET, NS>(m, p, ld, st, dg);
             __syncwarp();
@@ -815,7 +840,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
             dg.reset();
             const int north = ph - 1;
             const int cnt_ph = ph == 1 ? cnt1 : cnt2, ring_ph = ph == 1 ? ring1 : ring2;
-            const int64_t jbase = p.first[ph] + (ph == 1 ? tl1 : tl2) * kSpecTile + ttid * kSpecV;
+            const int64_t jbase = p.first[ph] + (ph == 1 ? tl1 : tl2) * GEO::kTile + ttid * kSpecV;
             int64_t jpart = -1;
             if (ring_ph != cnt_ph && team == 0) {      // partial tile of this grid, before its ring tiles
                 const int64_t j = jbase + (int64_t)(cnt_ph - 1) * jstride;
@@ -850,7 +875,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
                 }
                 mbar_wait(&fullU[bi], use & 1);
                 FastVec<kSpecV> m;
-                const LdStage ld{ring + (size_t)h * p.u_stage_bytes + toff};
+                const LdStage<GEO::kSlotBytes> ld{ring + (size_t)h * p.u_stage_bytes + toff};
                 const StPair st{j};
                 spec_uv_chain<SET, NS>(m, p, north, ld, st, dg);
                 __syncwarp();
@@ -982,8 +1007,8 @@ static bool spec_fill(const FusedPlan &p, SpecPlan &sp)
             if (sp.src[g][a]) u_slots = (a + 1 > u_slots) ? a + 1 : u_slots;
     // 227 KB per SM, 1 KB reserved per CTA, ~3-6 KB static (barriers, flag lists, diagnostics staging)
     const int budget = (NS == 1) ? 110 * 1024 : 220 * 1024;
-    sp.t_stage_bytes = t_slots * kSpecSlotBytes;
-    sp.u_stage_bytes = u_slots * kSpecSlotBytes;
+    sp.t_stage_bytes = t_slots * SpecGeom<NS>::kSlotBytes;
+    sp.u_stage_bytes = u_slots * SpecGeom<NS>::kSlotBytes;
     sp.t_stages = budget / sp.t_stage_bytes;
     sp.u_stages = budget / sp.u_stage_bytes;
     if (sp.t_stages > kSpecMaxStages) sp.t_stages = kSpecMaxStages;
@@ -997,7 +1022,10 @@ static bool spec_fill(const FusedPlan &p, SpecPlan &sp)
         }
         return a / x * b;
     };
-    const int teams = (NS == 1) ? 1 : 2;
+    const int teams = SpecGeom<NS>::kTeams;
+    // one barrier per (team, stage) pair: lcm(teams, stages) of them; give up a stage if that exceeds the barrier arrays
+    while (sp.t_stages > 2 && lcm(teams, sp.t_stages) > kSpecMaxBars) --sp.t_stages;
+    while (sp.u_stages > 2 && lcm(teams, sp.u_stages) > kSpecMaxBars) --sp.u_stages;
     sp.t_bars = lcm(teams, sp.t_stages);
     sp.u_bars = lcm(teams, sp.u_stages);
     return sp.t_stages >= 2 && sp.u_stages >= 2 && sp.t_bars <= kSpecMaxBars && sp.u_bars <= kSpecMaxBars;
@@ -1038,7 +1066,8 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     for (int g = 0; g < 3; ++g) {
         sp.first[g] = first[g];
         sp.end[g] = first[g] + cells[g];
-        sp.ntiles[g] = (int)((cells[g] + kSpecTile - 1) / kSpecTile);
+        const int tile = (p.S == 1) ? SpecGeom<1>::kTile : SpecGeom<2>::kTile;
+        sp.ntiles[g] = (int)((cells[g] + tile - 1) / tile);
     }
     sp.do_early = p.do_early;
     sp.has_bias = t.bias != nullptr;
@@ -1071,7 +1100,7 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     for (int g = 0; g < 3; ++g) {
         int n = 0;
         for (int k = 0; k < kSpecMaxSlots; ++k) n += sp.src[g][k] != nullptr;
-        sp.tx_bytes[g] = (uint32_t)n * kSpecSlotBytes;
+        sp.tx_bytes[g] = (uint32_t)n * (uint32_t)((p.S == 1) ? SpecGeom<1>::kSlotBytes : SpecGeom<2>::kSlotBytes);
     }
     sp.area[0] = t.area;
     sp.area[1] = p.uv[0].area;
