@@ -296,7 +296,8 @@ def main():
     launches0 = fc.info("launches")
     fc.set_option("profile_kernel", args.profile_stride)      # event pairs around every n-th fused launch
     sampler = ClockSampler(device)
-    sampler.start()
+    if os.environ.get("FC_BENCH_NO_SAMPLER") != "1":      # tuning aid: rule out the NVML polling as a perturbation
+        sampler.start()
     barrier()
     fc.event_record(0)
     for k in range(args.steps):
@@ -309,6 +310,8 @@ def main():
     fc.set_option("profile_kernel", 0)
     launches = fc.info("launches") - launches0
     exact_calls = fc.info("exact_path_calls")
+    if os.environ.get("FC_BENCH_PER_RANK") == "1":
+        sys.stderr.write("rank %d: %.4f ms/step, bracketed kernel %.4f ms, cells %d\n" % (rank, ms_total / args.steps, kern_ms / max(kern_cnt, 1), size))
     if dist:
         import torch
         t = torch.tensor([ms_total, kern_ms / max(kern_cnt, 1)], dtype=torch.float64)

@@ -899,22 +899,16 @@ __global__ void diag_combine_kernel(const double *__restrict__ chunk_out, int nc
 __global__ void diag_post_kernel(const double *__restrict__ diag_out, const __grid_constant__ PeerPost post, int n_active)
 {
     const int t = threadIdx.x;
-    if (t < n_active) {
-        const double s = diag_out[t], mn = diag_out[kDiagSlots + t], mx = diag_out[2 * kDiagSlots + t];
-        for (int r = 0; r < post.nranks; ++r) {
-            DiagMail *m = post.mail[r] + (size_t)post.parity * post.nranks + post.rank;
-            m->v[0][t] = s;
-            m->v[1][t] = mn;
-            m->v[2][t] = mx;
+    if (t >= n_active) return;
+    unsigned long long w[3][2];
+    for (int pl = 0; pl < 3; ++pl) diag_mail_pack(diag_out[pl * kDiagSlots + t], (unsigned int)post.seq, w[pl]);
+    for (int r = 0; r < post.nranks; ++r) {
+        DiagMail *m = post.mail[r] + (size_t)post.parity * post.nranks + post.rank;
+        for (int pl = 0; pl < 3; ++pl) {
+            __stcg(&m->w[pl][t][0], w[pl][0]);
+            __stcg(&m->w[pl][t][1], w[pl][1]);
         }
-        __threadfence_system();
     }
-    __syncthreads();
-    if (t == 0)
-        for (int r = 0; r < post.nranks; ++r) {
-            DiagMail *m = post.mail[r] + (size_t)post.parity * post.nranks + post.rank;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&m->seq), "l"(post.seq) : "memory");
-        }
 }
 
 int launch_diag_post(const double *diag_out, const PeerPost &post, int n_active, cudaStream_t stream)

@@ -3,14 +3,14 @@
 // One process per GPU.  Every rank allocates a mailbox (2 parities x nranks DiagMail records), exports it as a CUDA
 // IPC handle; the host exchanges the handles (MPI_Allgather in the Fortran host, torch.distributed/gloo in bench.py)
 // and every rank maps all mailboxes.  From then on the last CTA of each step's kernel stores the rank's result
-// vector into the mailbox of every rank with plain peer stores, fences at system scope and publishes the step's
-// sequence number (spec_kernel.cu: diag_finish; other paths: diag_post_kernel).  No collective launch, no extra
-// kernel, nothing competing with the persistent kernel for an SM.  fc_get_diagnostics folds the nranks records in
+// vector into the mailbox of every rank with plain peer stores of self-validating 8-byte words (32 data bits + the
+// step's 32-bit sequence number; no fence, no flag store) (spec_kernel.cu: diag_finish; other paths:
+// diag_post_kernel).  No collective launch, no extra kernel, nothing competing with the persistent kernel for an SM.  fc_get_diagnostics folds the nranks records in
 // rank order on the host, so all ranks see bit-identical global sums.  NCCL (nccl_dyn.cu) remains as the fallback
 // when IPC is unavailable.
 //
 // Double buffering: a record of step k is overwritten by step k+2; a reader that comes later than that gets an
-// error, never mixed data (the sequence numbers are checked before and after the copy).
+// error, never mixed data (every word carries its step's tag).
 #include "context.h"
 
 #include <string.h>
@@ -94,10 +94,11 @@ void p2p_next_post(fc_context *c, PeerPost &post)
     for (int r = 0; r < c->nranks; ++r) post.mail[r] = c->peer_mail[r];
 }
 
-// global diagnostics of the last step: wait until every rank's record of that step has arrived, fold in rank order
+// global diagnostics of the last step: wait until every needed word of every rank carries that step's tag, fold in rank order
 int p2p_fetch(fc_context *c, double *planes /* [3][kDiagSlots] */, int n_active, int level)
 {
     const int R = c->nranks, parity = (int)(c->diag_seq & 1ull);
+    const unsigned int want = (unsigned int)c->diag_seq;
     std::vector<DiagMail> host((size_t)R);
     const DiagMail *src = c->mailbox + (size_t)parity * R;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // our own record is posted
@@ -105,29 +106,38 @@ int p2p_fetch(fc_context *c, double *planes /* [3][kDiagSlots] */, int n_active,
     for (;;) {
         CUDA_TRY(c, cudaMemcpy(host.data(), src, sizeof(DiagMail) * R, cudaMemcpyDeviceToHost));
         bool all = true;
-        for (int r = 0; r < R; ++r) {
-            if (host[r].seq > c->diag_seq)
-                return fail(c, FC_ERR_STATE, "diagnostics of step %llu were overwritten: rank %d is already at step %llu "
-                            "(read the global diagnostics at most one step late)", c->diag_seq, r, host[r].seq);
-            all = all && host[r].seq == c->diag_seq;
-        }
+        for (int r = 0; r < R && all; ++r)
+            for (int pl = 0; pl < 3 && all; ++pl)
+                for (int k = 0; k < n_active && all; ++k)
+                    for (int h = 0; h < 2; ++h) {
+                        const unsigned int tag = (unsigned int)(host[r].w[pl][k][h] >> 32);
+                        if (tag == want) continue;
+                        if ((int)(tag - want) > 0)
+                            return fail(c, FC_ERR_STATE, "diagnostics of step %llu were overwritten: rank %d is already %d step(s) further "
+                                        "(read the global diagnostics at most one step late)", c->diag_seq, r, (int)(tag - want));
+                        all = false;      // not arrived yet
+                        break;
+                    }
         if (all) break;
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0)
             return fail(c, FC_ERR_NCCL, "peer diagnostics of step %llu did not arrive within 30 s", c->diag_seq);
         usleep(20);
     }
-    // every sequence number was seen BEFORE this copy started, so the records it reads are complete
-    CUDA_TRY(c, cudaMemcpy(host.data(), src, sizeof(DiagMail) * R, cudaMemcpyDeviceToHost));
-    for (int r = 0; r < R; ++r)
-        if (host[r].seq != c->diag_seq)
-            return fail(c, FC_ERR_STATE, "diagnostics of step %llu were overwritten while being read", c->diag_seq);
+    // every word of this snapshot validated itself: fold
+    auto val = [&](int r, int pl, int k) {
+        const unsigned long long b = (host[r].w[pl][k][0] & 0xffffffffull) | (host[r].w[pl][k][1] << 32);
+        double x;
+        memcpy(&x, &b, 8);
+        return x;
+    };
     for (int k = 0; k < n_active; ++k) {
-        double s = 0.0, mn = host[0].v[1][k], mx = host[0].v[2][k];
+        double s = 0.0, mn = val(0, 1, k), mx = val(0, 2, k);
         for (int r = 0; r < R; ++r) {
-            s += host[r].v[0][k];
+            s += val(r, 0, k);
             if (level >= 2) {
-                mn = host[r].v[1][k] < mn ? host[r].v[1][k] : mn;
-                mx = host[r].v[2][k] > mx ? host[r].v[2][k] : mx;
+                const double a = val(r, 1, k), b = val(r, 2, k);
+                mn = a < mn ? a : mn;
+                mx = b > mx ? b : mx;
             }
         }
         planes[0 * kDiagSlots + k] = s;

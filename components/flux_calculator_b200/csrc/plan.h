@@ -10,6 +10,7 @@
 #pragma once
 
 #include <stdint.h>
+#include <string.h>
 
 #include "formulas.cuh"
 
@@ -114,15 +115,23 @@ struct FusedUV {
 
 // Peer-memory exchange of the diagnostics (p2p_comm.cu): every rank owns a mailbox [parity][source rank] of DiagMail
 // records; the last CTA of a step's kernel stores the rank's result vector into the mailbox of EVERY rank over
-// NVLink (plain peer stores), fences, and publishes the step's sequence number.  Readers fold the records in rank
+// NVLink.  Every double travels as two self-validating 8-byte words (32 data bits + the step's 32-bit sequence number,
+// the layout of NCCL's LL protocol): an aligned 8-byte store is single-copy atomic, so no fence, no barrier and no
+// separate flag store are needed on the writer's side -- the stores just drain when the kernel ends -- and a reader
+// accepts a word only if its tag equals the sequence number it is waiting for.  Readers fold the records in rank
 // order, so all ranks obtain bit-identical global values.
 constexpr int kMaxPeers = 16;
 constexpr int kDiagSlotsFwd = (kMaxSurfaceTypes + 1) * 10;
 struct DiagMail {
-    double v[3][kDiagSlotsFwd];      // [sum|min|max][compact slot]
-    unsigned long long seq;          // step sequence number, written last (release, system scope)
-    unsigned long long pad;
+    unsigned long long w[3][kDiagSlotsFwd][2];      // [sum|min|max][compact slot][lo|hi]: (seq32 << 32) | 32 bits of the double
 };
+__host__ __device__ inline void diag_mail_pack(double x, unsigned int seq32, unsigned long long out[2])
+{
+    unsigned long long b;
+    memcpy(&b, &x, 8);
+    out[0] = ((unsigned long long)seq32 << 32) | (b & 0xffffffffull);
+    out[1] = ((unsigned long long)seq32 << 32) | (b >> 32);
+}
 struct PeerPost {
     int nranks, rank;                // nranks <= 1: off
     int parity, pad;

@@ -416,23 +416,23 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums<NS, DIAG
             p.diag_out[0 * kDiagSlots + cs] = s;
             p.diag_out[1 * kDiagSlots + cs] = mn;
             p.diag_out[2 * kDiagSlots + cs] = mx;
-            // compute -> exchange in one kernel: the result goes straight into every rank's mailbox over NVLink
-            for (int r = 0; r < p.post.nranks; ++r) {
-                DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
-                m->v[0][cs] = s;
-                m->v[1][cs] = mn;
-                m->v[2][cs] = mx;
+            // compute -> exchange in one kernel: the result goes straight into every rank's mailbox over NVLink, as
+            // self-validating 8-byte words (no fence, no flag store: see DiagMail)
+            if (p.post.nranks > 1) {
+                unsigned long long ws_[3][2];
+                diag_mail_pack(s, (unsigned int)p.post.seq, ws_[0]);
+                diag_mail_pack(mn, (unsigned int)p.post.seq, ws_[1]);
+                diag_mail_pack(mx, (unsigned int)p.post.seq, ws_[2]);
+                for (int r = 0; r < p.post.nranks; ++r) {
+                    DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+                        __stcg(&m->w[pl][cs][0], ws_[pl][0]);
+                        __stcg(&m->w[pl][cs][1], ws_[pl][1]);
+                    }
+                }
             }
         }
-    }
-    if (p.post.nranks > 1) {
-        __threadfence_system();          // the records are visible system-wide before ...
-        consumer_barrier<NS>();
-        if (tid == 0)
-            for (int r = 0; r < p.post.nranks; ++r) {      // ... the sequence number that publishes them
-                DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&m->seq), "l"(p.post.seq) : "memory");
-            }
     }
     if (tid == 0) *p.counter = 0u;      // ready for the next launch (same stream)
 }
