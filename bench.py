@@ -207,6 +207,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--prefetch", type=int, default=None, help="L2 prefetch distance in blocks (tuning)")
     ap.add_argument("--staged", type=int, default=None, help="0/1: forbid/allow the staged kernel (tuning)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default, BASELINE.json configs[3]: the 10^7-cell grid is fixed and sharded over the GPUs) or weak "
+                         "(every GPU gets the workload's full cell count)")
     ap.add_argument("--profile-stride", type=int, default=8,
                     help="bracket every n-th fused launch with an event pair for the roofline's kernel time (an event between two "
                          "launches switches their programmatic overlap off, so not every launch is bracketed)")
@@ -237,6 +240,8 @@ def main():
     fset, n_total, S, bias, avg, diag, desc = WORKLOADS[args.workload]
     if args.cells:
         n_total = args.cells
+    if args.scaling == "weak":
+        n_total *= world
     if args.diag is not None:
         diag = bool(args.diag)
     off, size = m.shard_range(n_total, rank, world, 512)
@@ -424,7 +429,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s: %s" % (args.workload, desc), "cells_per_grid": n_total, "formula_set": fset,
                        "surface_types": S, "bias": bias, "averaging": avg, "diagnostics": diag,

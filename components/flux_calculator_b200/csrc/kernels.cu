@@ -33,7 +33,7 @@ using Exact = ExactVec<V>;
 struct LdGlobal {
     static constexpr bool kFull = true;
     int64_t j;
-    __device__ __forceinline__ V2 load(const double *__restrict__ p, int) const
+    __device__ __forceinline__ V2 load(const double *__restrict__ p) const
     {
         static_assert(V == 2, "128-bit path assumes 2 cells per thread");
         const double2 t = __ldg(reinterpret_cast<const double2 *>(p + j));
@@ -52,7 +52,7 @@ struct LdGuard {
     static constexpr bool kFull = false;
     int64_t j;
     int nv;
-    __device__ __forceinline__ V2 load(const double *__restrict__ p, int) const
+    __device__ __forceinline__ V2 load(const double *__restrict__ p) const
     {
         V2 r;
 #pragma unroll
@@ -73,11 +73,11 @@ template <class LD>
 struct Cached {
     const double *ptr = nullptr;
     V2 val;
-    __device__ __forceinline__ const V2 &get(const LD &ld, const double *p, int slot)
+    __device__ __forceinline__ const V2 &get(const LD &ld, const double *p)
     {
         if (p != ptr) {
             ptr = p;
-            if (p) val = ld.load(p, slot);
+            if (p) val = ld.load(p);
         }
         return val;
     }
@@ -238,9 +238,9 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv
     V2 rsdd, area;
     const bool has_bias = p.do_normal && t.bias != nullptr;
     const bool has_rsdr = p.do_normal && t.rsdd != nullptr;
-    if (has_bias) in.bias_ = ld.load(t.bias, t.s_bias);
-    if (has_rsdr) rsdd = ld.load(t.rsdd, t.s_rsdd);
-    if (DIAG) area = ld.load(t.area, t.s_area);
+    if (has_bias) in.bias_ = ld.load(t.bias);
+    if (has_rsdr) rsdd = ld.load(t.rsdd);
+    if (DIAG) area = ld.load(t.area);
     V2 aQ = vzero(), aM = vzero(), aL = vzero(), aH = vzero(), aR = vzero(), aS = vzero();   // type-0 averages
 
     auto per_type = [&](const int i) {
@@ -249,19 +249,19 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv
         TOut o;
         if (LD::kFull || nv) {
             // all loads of this surface type up front (memory-level parallelism), then arithmetic
-            if (ty.fare) fare = ld.load(ty.fare, ty.s_fare);
-            in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
+            if (ty.fare) fare = ld.load(ty.fare);
+            in.tsur_ = cTSUR.get(ld, ty.tsur);
             if (p.do_normal) {
-                in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
-                in.qatm_ = cQATM.get(ld, ty.qatm, ty.s_qatm);
-                in.tatm_ = cTATM.get(ld, ty.tatm, ty.s_tatm);
-                in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
-                in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
-                in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
-                in.aev_ = cAEV.get(ld, ty.a_evap, ty.s_aev);
-                in.ase_ = cASE.get(ld, ty.a_sens, ty.s_ase);
-                in.patm_ = cPATM.get(ld, ty.patm, ty.s_patm);
-                if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
+                in.psur_ = cPSUR.get(ld, ty.psur);
+                in.qatm_ = cQATM.get(ld, ty.qatm);
+                in.tatm_ = cTATM.get(ld, ty.tatm);
+                in.uatm_ = cUATM.get(ld, ty.uatm);
+                in.vatm_ = cVATM.get(ld, ty.vatm);
+                in.fice_ = cFICE.get(ld, ty.fice);
+                in.aev_ = cAEV.get(ld, ty.a_evap);
+                in.ase_ = cASE.get(ld, ty.a_sens);
+                in.patm_ = cPATM.get(ld, ty.patm);
+                if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in);
             }
             if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
                 o = t_type_exact(p, i, in, has_bias);             // redo these cells with the IEEE routines
@@ -372,7 +372,7 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
     Cached<LD> cPSUR, cUATM, cVATM, cAMOM, cFICE, cTSUR;
     UVIn in;
     V2 area;
-    if (DIAG) area = ld.load(g.area, g.s_area);
+    if (DIAG) area = ld.load(g.area);
     V2 aQ = vzero(), aM = vzero();
 
     auto per_type = [&](const int i) {
@@ -380,14 +380,14 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
         V2 fare;
         UVOut o;
         if (LD::kFull || nv) {
-            if (ty.fare) fare = ld.load(ty.fare, ty.s_fare);
-            in.fice_ = cFICE.get(ld, ty.fice, ty.s_fice);
-            in.psur_ = cPSUR.get(ld, ty.psur, ty.s_psur);
-            in.tsur_ = cTSUR.get(ld, ty.tsur, ty.s_tsur);
-            in.uatm_ = cUATM.get(ld, ty.uatm, ty.s_uatm);
-            in.vatm_ = cVATM.get(ld, ty.vatm, ty.s_vatm);
-            in.amom_ = cAMOM.get(ld, ty.a_mom, ty.s_amom);
-            if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in, ty.s_qsur_in);
+            if (ty.fare) fare = ld.load(ty.fare);
+            in.fice_ = cFICE.get(ld, ty.fice);
+            in.psur_ = cPSUR.get(ld, ty.psur);
+            in.tsur_ = cTSUR.get(ld, ty.tsur);
+            in.uatm_ = cUATM.get(ld, ty.uatm);
+            in.vatm_ = cVATM.get(ld, ty.vatm);
+            in.amom_ = cAMOM.get(ld, ty.a_mom);
+            if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in);
             if (uv_type_math<Fast>(p, ty, in, g.north, o)) o = uv_type_exact(p, which, i, in);
             if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
             if (ty.m_mom != M_NONE) ld.store(ty.mom, o.mom);

@@ -71,7 +71,6 @@ struct OpList {
 // ---------------------------------------------------------------------------------------------
 // fused plan
 // ---------------------------------------------------------------------------------------------
-// s_* : unused since the staged generic kernel was replaced by spec_kernel.cu (kept so the plan layout is stable)
 struct FusedTType {     // one surface type on the t grid
     const double *fice, *psur, *tsur, *qatm, *tatm, *patm, *uatm, *vatm;
     const double *a_evap;    // AMOI (CCLM) or CMOI (MOM5)
@@ -81,15 +80,12 @@ struct FusedTType {     // one surface type on the t grid
     double *qsur, *meva, *hlat, *hsen, *rbbr, *rsdr;
     int m_qsur, m_meva, m_hlat, m_hsen, m_rbbr, pad;
     double latent_heat;      // L_v (water) or L_s (ice)
-    signed char s_fice, s_psur, s_tsur, s_qatm, s_tatm, s_patm, s_uatm, s_vatm, s_aev, s_ase, s_qsur_in, s_fare;
-    signed char spad[4];
 };
 
 struct FusedUVType {    // one surface type on the u or v grid
     const double *fice, *psur, *tsur, *a_mom, *uatm, *vatm, *qsur_in, *fare;
     double *qsur, *mom;      // mom = UMOM on the u grid, VMOM on the v grid
     int m_qsur, m_mom;
-    signed char s_fice, s_psur, s_tsur, s_amom, s_uatm, s_vatm, s_qsur_in, s_fare;
 };
 
 struct FusedT {
@@ -99,7 +95,6 @@ struct FusedT {
     const double *area;      // cell areas (diagnostics) or null
     // type-0 area-fraction averages (null = not averaged)
     double *avg_qsur, *avg_meva, *avg_hlat, *avg_hsen, *avg_rbbr, *avg_rsdr;
-    signed char s_rsdd, s_bias, s_area, spad[5];
     FusedTType ty[kMaxSurfaceTypes];
 };
 
@@ -109,7 +104,6 @@ struct FusedUV {
     int pad;
     const double *area;
     double *avg_qsur, *avg_mom;
-    signed char s_area, spad[7];
     FusedUVType ty[kMaxSurfaceTypes];
 };
 
