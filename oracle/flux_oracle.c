@@ -1,7 +1,13 @@
 /*
  * flux_oracle.c -- CPU restatement of the IOW-ESM flux_calculator hot path.
- * TEST INFRASTRUCTURE ONLY (see flux_oracle.h).  Parity pin: tests/golden/ (source-
- * interpreted vectors + mpmath KATs); no reference binary could be run here.
+ * TEST INFRASTRUCTURE ONLY (see flux_oracle.h): only tests/, __graft_entry__.smoke() and the
+ * CPU legs of bench.py may load it; the product library never does.
+ * PARITY UNPINNED by any reference binary or reference-shipped vector: the reference (Fortran +
+ * MPI + netCDF + OASIS3-MCT) cannot be compiled in this image and ships no tests.  What pins this
+ * file instead: tests/golden/flux_lib_golden.json, produced by tests/golden/make_golden.py, which
+ * parses and evaluates the reference's own Fortran text of flux_lib/ and the call-site wiring of
+ * flux_calculator_calculate.F90 (bit-for-bit agreement), plus 50-digit mpmath known answers
+ * (tests/golden/kat_mpmath.json).  See DESIGN.md section 3.
  *
  * All arithmetic is binary64 in the Fortran evaluation order (left to right within
  * equal precedence, parentheses as written in the reference).  Compile with
