@@ -264,57 +264,6 @@ __device__ __forceinline__ void diag_cells(double &s, double &mn, double &mx, in
     }
 }
 
-// running diagnostics of one phase: NQ quantities (Q0 ..) of every surface type (and of the averages with two types)
-template <int NS, int DIAG, int NQ, int Q0>
-struct DiagAcc {
-    static constexpr int kTypes = (NS == 1) ? 1 : NS + 1;
-    static constexpr int kN = kTypes * NQ;
-    double s[kN], mn[DIAG >= 2 ? kN : 1], mx[DIAG >= 2 ? kN : 1];
-    S2 area;
-    int nv;      // valid cells of the tile being accumulated (2 except in the partial tile)
-    static __device__ __forceinline__ constexpr int idx(int type, int q) { return (NS == 1 ? 0 : type * NQ) + (q - Q0); }
-    __device__ __forceinline__ void reset()
-    {
-        nv = kSpecV;
-#pragma unroll
-        for (int k = 0; k < kN; ++k) {
-            s[k] = 0.0;
-            if (DIAG >= 2) {
-                mn[k] = DBL_MAX;
-                mx[k] = -DBL_MAX;
-            }
-        }
-    }
-    // full tile
-    __device__ __forceinline__ void operator()(int type, int q, const S2 &x)
-    {
-        if (DIAG == 0) return;
-        const int k = idx(type, q);
-        if constexpr (DIAG >= 2) {
-            diag_pair(s[k], mn[k], mx[k], DIAG, area.v[0], area.v[1], x.v[0], x.v[1]);
-        } else {
-            double dm = 0.0, dM = 0.0;
-            diag_pair(s[k], dm, dM, DIAG, area.v[0], area.v[1], x.v[0], x.v[1]);
-        }
-    }
-};
-template <int NS, int DIAG, int NQ, int Q0>
-struct DiagAccGuard {    // the same accumulators fed from a partial tile
-    DiagAcc<NS, DIAG, NQ, Q0> &a;
-    int nv;
-    __device__ __forceinline__ void operator()(int type, int q, const S2 &x)
-    {
-        if (DIAG == 0) return;
-        const int k = DiagAcc<NS, DIAG, NQ, Q0>::idx(type, q);
-        if constexpr (DIAG >= 2) {
-            diag_cells(a.s[k], a.mn[k], a.mx[k], DIAG, a.area.v[0], a.area.v[1], x.v[0], x.v[1], nv);
-        } else {
-            double dm = 0.0, dM = 0.0;
-            diag_cells(a.s[k], dm, dM, DIAG, a.area.v[0], a.area.v[1], x.v[0], x.v[1], nv);
-        }
-    }
-};
-
 // warp tree of one quantity; lane 0 leaves the warp's value in the CTA's staging area
 template <int NS, int DIAG>
 __device__ __forceinline__ void diag_flush_one(WarpSums<NS, DIAG> &ws, int wsi, double s, double mn, double mx)
@@ -336,6 +285,122 @@ __device__ __forceinline__ void diag_flush_one(WarpSums<NS, DIAG> &ws, int wsi, 
         }
     }
 }
+
+// Running diagnostics of one phase: NQ quantities (Q0 ..) of every surface type (and of the averages with two types).
+//   REG = true  (one surface type): per-THREAD running values in registers over all tiles of the thread, one warp
+//                tree per quantity at the end of the phase;
+//   REG = false (two surface types: 17 sums, or 51 values with min/max, do not fit the register file next to the
+//                chain): one warp tree per quantity per TILE, lane 0 accumulates the warp's value in shared memory.
+// Both are deterministic (static tile schedule, fixed trees).
+constexpr int kDiagAccMax = (kSpecMaxNS + 1) * 6;      // accumulators of the t phase with two types
+template <int NS, int DIAG, int NQ, int Q0, bool REG = (NS == 1)>
+struct DiagAcc;
+
+template <int NS, int DIAG, int NQ, int Q0>
+struct DiagAcc<NS, DIAG, NQ, Q0, true> {
+    static constexpr int kN = NQ;
+    double s[kN], mn[DIAG >= 2 ? kN : 1], mx[DIAG >= 2 ? kN : 1];
+    S2 area;
+    static __device__ __forceinline__ constexpr int idx(int, int q) { return q - Q0; }
+    __device__ __forceinline__ void init(double *) {}
+    __device__ __forceinline__ void reset()
+    {
+#pragma unroll
+        for (int k = 0; k < kN; ++k) {
+            s[k] = 0.0;
+            if (DIAG >= 2) {
+                mn[k] = DBL_MAX;
+                mx[k] = -DBL_MAX;
+            }
+        }
+    }
+    __device__ __forceinline__ void add_cells(int type, int q, const S2 &x, int nv)      // nv valid cells (2 except in the partial tile)
+    {
+        if (DIAG == 0) return;
+        const int k = idx(type, q);
+        if constexpr (DIAG >= 2) {
+            diag_cells(s[k], mn[k], mx[k], DIAG, area.v[0], area.v[1], x.v[0], x.v[1], nv);
+        } else {
+            double dm = 0.0, dM = 0.0;
+            diag_cells(s[k], dm, dM, DIAG, area.v[0], area.v[1], x.v[0], x.v[1], nv);
+        }
+    }
+    __device__ __forceinline__ void operator()(int type, int q, const S2 &x) { add_cells(type, q, x, kSpecV); }
+    // end of the phase: q0 = first quantity of the phase in the staging area (DQ_QSUR_T / _U / _V)
+    __device__ __forceinline__ void flush(WarpSums<NS, DIAG> &ws, int q0)
+    {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            diag_flush_one<NS, DIAG>(ws, ws_index<NS>(1, q0 + q), s[q], DIAG >= 2 ? mn[DIAG >= 2 ? q : 0] : 0.0, DIAG >= 2 ? mx[DIAG >= 2 ? q : 0] : 0.0);
+    }
+};
+
+template <int NS, int DIAG, int NQ, int Q0>
+struct DiagAcc<NS, DIAG, NQ, Q0, false> {
+    static constexpr int kN = (NS + 1) * NQ;
+    static_assert(kN <= kDiagAccMax && kN <= 32, "one lane per accumulator at reset / flush");
+    double *acc;      // this warp's [plane][kDiagAccMax] in shared memory
+    S2 area;
+    static __device__ __forceinline__ constexpr int idx(int type, int q) { return type * NQ + (q - Q0); }
+    __device__ __forceinline__ void init(double *warp_rows) { acc = warp_rows; }
+    __device__ __forceinline__ void reset()
+    {
+        if (DIAG == 0) return;
+        const int lane = threadIdx.x & 31;
+        if (lane < kN) {
+            acc[lane] = 0.0;
+            if (DIAG >= 2) {
+                acc[kDiagAccMax + lane] = DBL_MAX;
+                acc[2 * kDiagAccMax + lane] = -DBL_MAX;
+            }
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void add_cells(int type, int q, const S2 &x, int nv)
+    {
+        if (DIAG == 0) return;
+        const int k = idx(type, q);
+        double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+        diag_cells(s, mn, mx, DIAG, area.v[0], area.v[1], x.v[0], x.v[1], nv);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s = add(s, __shfl_down_sync(0xffffffffu, s, off));
+            if (DIAG >= 2) {
+                mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
+                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+            }
+        }
+        if ((threadIdx.x & 31) == 0) {
+            acc[k] = add(acc[k], s);
+            if (DIAG >= 2) {
+                acc[kDiagAccMax + k] = fmin(acc[kDiagAccMax + k], mn);
+                acc[2 * kDiagAccMax + k] = fmax(acc[2 * kDiagAccMax + k], mx);
+            }
+        }
+    }
+    __device__ __forceinline__ void operator()(int type, int q, const S2 &x) { add_cells(type, q, x, kSpecV); }
+    __device__ __forceinline__ void flush(WarpSums<NS, DIAG> &ws, int q0)
+    {
+        __syncwarp();
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane < kN) {
+            const int wsi = ws_index<NS>(lane / NQ, q0 + lane % NQ);
+            ws.v[0][wsi][w] = acc[lane];
+            if constexpr (DIAG >= 2) {
+                ws.v[1][wsi][w] = acc[kDiagAccMax + lane];
+                ws.v[2][wsi][w] = acc[2 * kDiagAccMax + lane];
+            }
+        }
+        __syncwarp();
+    }
+};
+
+template <int NS, int DIAG, int NQ, int Q0>
+struct DiagAccGuard {    // the same accumulators fed from a partial tile
+    DiagAcc<NS, DIAG, NQ, Q0> &a;
+    int nv;
+    __device__ __forceinline__ void operator()(int type, int q, const S2 &x) { a.add_cells(type, q, x, nv); }
+};
 
 template <int NS>
 __device__ __forceinline__ void consumer_barrier()
@@ -626,6 +691,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     __shared__ int flagged[GEO::kWarps][kSpecBadCap];
     __shared__ int nflagged[GEO::kWarps];
     __shared__ WarpSums<NS, DIAG> ws;
+    __shared__ double wacc[(NS > 1 && DIAG) ? GEO::kWarps : 1][(NS > 1 && DIAG) ? (DIAG >= 2 ? 3 : 1) * kDiagAccMax : 1];
     __shared__ int is_last;
 
     const int NT = p.t_stages, NUS = p.u_stages, LT = p.t_bars, LU = p.u_bars;
@@ -763,6 +829,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     const int64_t jstride = (int64_t)G * GEO::kTile;
     {   // t phase
         DiagAcc<NS, DIAG, 6, DQ_QSUR_T> dg;
+        dg.init(wacc[(NS > 1 && DIAG) ? warp : 0]);
         dg.reset();
         const int64_t jbase = p.first[0] + tl0 * GEO::kTile + ttid * kSpecV;      // this thread's cells of ring tile 0
         int64_t jpart = -1;
@@ -822,14 +889,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
             if (lane == 0) nflagged[warp] = 0;
             __syncwarp();
         } else if (DIAG) {
-#pragma unroll
-            for (int ty = (NS == 1 ? 1 : 0); ty <= NS; ++ty)
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int k = DiagAcc<NS, DIAG, 6, DQ_QSUR_T>::idx(ty, q);
-                    diag_flush_one<NS, DIAG>(ws, ws_index<NS>(ty, DQ_QSUR_T + q), dg.s[k], DIAG >= 2 ? dg.mn[DIAG >= 2 ? k : 0] : 0.0,
-                                             DIAG >= 2 ? dg.mx[DIAG >= 2 ? k : 0] : 0.0);
-                }
+            dg.flush(ws, DQ_QSUR_T);
         }
     }
     {   // u phase, then v phase: same code, same carving, tile counter k runs across both grids
@@ -837,6 +897,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
 #pragma unroll 1
         for (int ph = 1; ph < 3; ++ph) {
             DiagAcc<NS, DIAG, 2, DQ_QSUR_U> dg;
+            dg.init(wacc[(NS > 1 && DIAG) ? warp : 0]);
             dg.reset();
             const int north = ph - 1;
             const int cnt_ph = ph == 1 ? cnt1 : cnt2, ring_ph = ph == 1 ? ring1 : ring2;
@@ -902,15 +963,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
                 if (lane == 0) nflagged[warp] = 0;
                 __syncwarp();
             } else if (DIAG) {
-                const int q0 = north ? DQ_QSUR_V : DQ_QSUR_U;
-#pragma unroll
-                for (int ty = (NS == 1 ? 1 : 0); ty <= NS; ++ty)
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int k = DiagAcc<NS, DIAG, 2, DQ_QSUR_U>::idx(ty, DQ_QSUR_U + q);
-                        diag_flush_one<NS, DIAG>(ws, ws_index<NS>(ty, q0 + q), dg.s[k], DIAG >= 2 ? dg.mn[DIAG >= 2 ? k : 0] : 0.0,
-                                                 DIAG >= 2 ? dg.mx[DIAG >= 2 ? k : 0] : 0.0);
-                    }
+                dg.flush(ws, north ? DQ_QSUR_V : DQ_QSUR_U);
             }
         }
     }
@@ -1005,8 +1058,9 @@ static bool spec_fill(const FusedPlan &p, SpecPlan &sp)
     for (int g = 1; g < 3; ++g)
         for (int a = 0; a < L::NUV; ++a)
             if (sp.src[g][a]) u_slots = (a + 1 > u_slots) ? a + 1 : u_slots;
-    // 227 KB per SM, 1 KB reserved per CTA, ~3-6 KB static (barriers, flag lists, diagnostics staging)
-    const int budget = (NS == 1) ? 110 * 1024 : 220 * 1024;
+    // 227 KB per SM, 1 KB reserved per CTA, static shared memory: barriers + flag lists (2 KB) and the diagnostics
+    // staging (one type: <= 2 KB; two types: 6 KB with sums, 18 KB with min/max)
+    const int budget = (NS == 1) ? 108 * 1024 : (sp.diag >= 2 ? 204 * 1024 : 216 * 1024);
     sp.t_stage_bytes = t_slots * SpecGeom<NS>::kSlotBytes;
     sp.u_stage_bytes = u_slots * SpecGeom<NS>::kSlotBytes;
     sp.t_stages = budget / sp.t_stage_bytes;
@@ -1038,9 +1092,6 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     const FusedT &t = p.t;
     if (t.avg_qsur || p.uv[0].avg_qsur || p.uv[1].avg_qsur) return false;
     if (p.S == 1 && (t.avg_meva || t.avg_hlat || t.avg_hsen || t.avg_rbbr || t.avg_rsdr || p.uv[0].avg_mom || p.uv[1].avg_mom)) return false;
-    // two surface types with diagnostics: 17 (sums) to 51 (sums + min/max) running accumulators per thread do not fit the
-    // register file next to the chain (measured: 712 bytes of spills, 1.31 ms against 0.99 ms on the direct-load kernel)
-    if (p.S > 1 && p.diag >= 1) return false;
     int set = -1;
     for (int i = 0; i < p.S; ++i) {
         const FusedTType &T = t.ty[i];
@@ -1164,14 +1215,8 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
 template <int SET, int NS>
 static cudaError_t spec_launch_d(const SpecPlan &sp, int grid, cudaStream_t stream)
 {
-    if (sp.diag >= 2) {
-        if constexpr (NS == 1) return spec_launch_t<SET, NS, 2>(sp, grid, stream);
-        else return cudaErrorInvalidValue;      // spec_build refuses this combination
-    }
-    if (sp.diag == 1) {
-        if constexpr (NS == 1) return spec_launch_t<SET, NS, 1>(sp, grid, stream);
-        else return cudaErrorInvalidValue;
-    }
+    if (sp.diag >= 2) return spec_launch_t<SET, NS, 2>(sp, grid, stream);
+    if (sp.diag == 1) return spec_launch_t<SET, NS, 1>(sp, grid, stream);
     return spec_launch_t<SET, NS, 0>(sp, grid, stream);
 }
 

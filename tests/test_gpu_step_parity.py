@@ -306,7 +306,7 @@ def test_chunked_host_pipeline_with_diagnostics(fcmod, S, staged):
 
 
 @pytest.mark.parametrize("fset", ["CCLM", "MOM5", "RCO"])
-@pytest.mark.parametrize("level", [0, 1])
+@pytest.mark.parametrize("level", [0, 1, 2])
 def test_spec_kernel_two_surface_types_long_schedule(fcmod, fset, level):
     """two surface types: one CTA per SM, two consumer teams sharing the ring (one barrier per (team, stage) pair);
     several tiles per team and per stage so that the barrier phases wrap, ragged remainders, averaging of the sent
@@ -316,7 +316,7 @@ def test_spec_kernel_two_surface_types_long_schedule(fcmod, fset, level):
     sc = Scenario(fset, n=n, S=2, bias=True, averaging=True)
     _, o_out, d_out, _, _ = run_both(fcmod, sc, "device", staged=0, diagnostics=level)
     fc, _, s_out, _, _ = run_both(fcmod, sc, "device", staged=2, diagnostics=level)
-    assert fc.info("spec_kernel") == (1 if level == 0 else 0)      # with diagnostics two types stay on the direct-load kernel
+    assert fc.info("spec_kernel") == 1
     compare(sc, o_out, s_out)
     if level:
         _diag_check(fc, sc, s_out, level)
