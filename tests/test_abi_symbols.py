@@ -113,3 +113,25 @@ def test_product_never_references_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".F90", "Makefile")):
                 text = open(os.path.join(dp, fn), errors="replace").read()
                 assert "oracle_py" not in text and "flux_oracle" not in text and "liboracle" not in text, os.path.join(dp, fn)
+
+
+def test_header_is_strict_c99_and_a_c_host_links(tmp_path):
+    """the boundary is a C ABI: the header must compile as plain C (no C++-isms) and a C host must link against the
+    library and call a non-compute entry point without a GPU"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "host.c"
+    src.write_text('#include "fluxcalc.h"\n#include <string.h>\n'
+                   'int main(void) {\n'
+                   '  int64_t off = 0, size = 0;\n'
+                   '  if (fc_version() != FC_VERSION) return 1;\n'
+                   '  if (fc_shard_range(1000000, 3, 8, 512, &off, &size) != FC_OK) return 2;\n'
+                   '  if (off != 3 * 124928 || size != 124928) return 3;\n'
+                   '  if (fc_current_month(19611231, 86400) != 1) return 4;\n'
+                   '  if (strcmp(fc_var_name(fc_var_index("TSUR")), "TSUR") != 0) return 5;\n'
+                   '  return 0;\n}\n')
+    libdir = os.path.join(root, "components", "flux_calculator_b200")
+    exe = tmp_path / "host"
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-lfluxcalc_b200", "-Wl,-rpath," + libdir])
+    assert subprocess.run([str(exe)]).returncode == 0

@@ -172,3 +172,62 @@ def test_namelist_and_corrections_drive_a_step(fcmod, nml, tmp_path):
     warn = fc.load_corrections(tmp_path, grid_offset=0, reference_start_quirk=True)
     assert warn.count("Unset correction") == 12
     fc.close()
+
+
+def test_namelist_parser_fuzz(tmp_path):
+    """random assignments in every supported form (whole array, element + value list, sections, r*c repeats, null
+    values, comments, either quote) against a direct model of Fortran's array-element-order semantics"""
+    import random
+    import components.flux_calculator_b200 as m
+    rnd = random.Random(12345)
+    words = ["CCLM", "MOM5", "RCO", "none", "zero", "copy", "water", "ice", "it''s", "a b"]
+    for trial in range(25):
+        model = {}
+        lines = ["&input"]
+        for _ in range(rnd.randint(1, 8)):
+            form = rnd.choice(["element", "section_row", "section_col", "whole"])
+            if form == "element":
+                i, j = rnd.randint(1, 10), rnd.randint(1, 10)
+                targets = list(range((i - 1) + 10 * (j - 1), 100))
+                lhs = "a(%d,%d)" % (i, j)
+            elif form == "section_row":
+                i, lo, hi = rnd.randint(1, 10), rnd.randint(1, 5), rnd.randint(5, 10)
+                targets = [(i - 1) + 10 * (j - 1) for j in range(lo, hi + 1)]
+                lhs = "A(%d, %d:%d)" % (i, lo, hi) if rnd.random() < 0.7 else ("a(%d,:)" % i)
+                if lhs.endswith(":)"):
+                    targets = [(i - 1) + 10 * (j - 1) for j in range(1, 11)]
+            elif form == "section_col":
+                j = rnd.randint(1, 10)
+                targets = [(i - 1) + 10 * (j - 1) for i in range(1, 11)]
+                lhs = "a(:,%d)" % j
+            else:
+                targets, lhs = list(range(100)), "a"
+            nvals = rnd.randint(1, min(6, len(targets)))
+            parts, k = [], 0
+            while k < nvals:
+                kind = rnd.choice(["value", "null", "repeat"])
+                w = rnd.choice(words)
+                q = rnd.choice("'\"")
+                lit = q + (w if q == "'" else w.replace("''", "'")) + q
+                val = w.replace("''", "'")
+                if kind == "value":
+                    parts.append(lit)
+                    model[targets[k]] = val
+                    k += 1
+                elif kind == "null" and parts:
+                    parts.append("")
+                    k += 1
+                elif kind == "repeat":
+                    r = rnd.randint(1, max(1, min(3, nvals - k)))
+                    parts.append("%d*%s" % (r, lit))
+                    for _ in range(r):
+                        model[targets[k]] = val
+                        k += 1
+            sep = rnd.choice([", ", " , ", ","])
+            lines.append("  %s = %s%s" % (lhs, sep.join(parts), rnd.choice(["", "   ! comment with 'quotes' and = signs", ","])))
+        lines.append("/")
+        path = tmp_path / ("f%d.nml" % trial)
+        path.write_text("\n".join(lines) + "\n")
+        for lin in rnd.sample(range(100), 30) + list(model)[:20]:
+            got = m.namelist_get(path, "input", "a", (10, 10), (lin % 10 + 1, lin // 10 + 1))
+            assert got == model.get(lin), (trial, lin, got, model.get(lin), path.read_text())
