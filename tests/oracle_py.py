@@ -131,13 +131,16 @@ class Oracle:
 
 
 def ulp_diff(a, b):
-    """element-wise distance in units in the last place between float64 arrays (0 for bit-equal; both NaN -> 0)"""
+    """element-wise distance in units in the last place between float64 arrays (0 only for bit-equal values, with
+    +0 == -0; both NaN -> 0).  Exact integer arithmetic on the ordered bit patterns (a float64 detour would lose the
+    low 9 bits of the 63-bit patterns and hide differences of up to 255 ulp)."""
     a = np.ascontiguousarray(a, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
     ia = a.view(np.int64).copy()
     ib = b.view(np.int64).copy()
-    ia = np.where(ia < 0, np.int64(-2**63) - ia, ia)
+    ia = np.where(ia < 0, np.int64(-2**63) - ia, ia)      # negative floats: mirror so that the integers are ordered like the reals
     ib = np.where(ib < 0, np.int64(-2**63) - ib, ib)
-    d = np.abs(ia.astype(np.float64) - ib.astype(np.float64))
+    hi, lo = np.maximum(ia, ib), np.minimum(ia, ib)
+    d = (hi.astype(np.uint64) - lo.astype(np.uint64)).astype(np.float64)      # exact below 2^53, which is all we care about
     both_nan = np.isnan(a) & np.isnan(b)
     return np.where(both_nan, 0.0, d)
