@@ -32,6 +32,7 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     # name: (formula_set, cells per grid, S, bias, averaging, diagnostics, description)
+    "C1": ("CCLM", 20_000, 1, False, False, False, "Baltic stand-in 20k cells/grid, CCLM set, single instance (BASELINE configs[0]: the reference's own CPU-runnable case; use --impl reference)"),
     "C2": ("MOM5", 20_000, 1, True, False, False, "Baltic stand-in 20k cells/grid, MOM5 coefficients + monthly evaporation bias"),
     "C3": ("RCO", 1_000_000, 1, False, False, False, "RCO (Meier 1999) formula set, 1e6 cells/grid"),
     "C4": ("CCLM", 10_000_000, 1, True, False, True, "1e7 cells/grid, CCLM set, all fluxes fused + bias + diagnostics (NCCL all-reduce for N>1)"),
