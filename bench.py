@@ -282,6 +282,7 @@ def main():
                     raise SystemExit("bench.py: peer mailboxes connected on some ranks only")
                 comm_used = "nccl"
         if comm_used == "nccl":
+            os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line only)
             uid = [m.comm_get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             fc.comm_init(uid[0], rank, world)
