@@ -7,7 +7,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <set>
+#include <unordered_map>
 
 using namespace fc;
 
@@ -15,7 +17,7 @@ namespace fc {
 thread_local std::string g_last_error;
 int nccl_allreduce_diag(fc_context *ctx);   // nccl_dyn.cu
 void p2p_destroy(fc_context *ctx);          // p2p_comm.cu
-void p2p_next_post(fc_context *ctx, PeerPost &post);
+void p2p_make_post(fc_context *ctx, PeerPost &post);
 int p2p_fetch(fc_context *ctx, double *planes, int n_active, int level);
 void nccl_destroy(fc_context *ctx);
 }  // namespace fc
@@ -175,17 +177,66 @@ extern "C" int fc_shard_range(int64_t n, int rank, int nranks, int64_t align, in
     return FC_OK;
 }
 
+// Device arrays handed out by the library start at STAGGERED offsets inside their allocation (option env
+// FC_ALLOC_STAGGER = bytes, a multiple of 256; the k-th allocation is shifted by (k mod 32) * stagger): equally sized
+// arrays allocated back to back would otherwise all sit at the same offset of their 2 MB pages, and the 20-30 streams
+// a tile reads and writes in lock step would walk the DRAM channels in phase.
+namespace {
+std::mutex g_alloc_mu;
+std::unordered_map<void *, void *> g_alloc_base;      // returned pointer -> cudaMalloc pointer
+int64_t alloc_stagger()
+{
+    static const int64_t v = [] {
+        const char *e = getenv("FC_ALLOC_STAGGER");
+        int64_t x = e ? atoll(e) : 0;
+        return x < 0 ? 0 : (x & ~int64_t(255));
+    }();
+    return v;
+}
+unsigned g_alloc_count = 0;
+}  // namespace
+
+namespace fc {
+cudaError_t staggered_malloc(void **dptr, size_t nbytes)
+{
+    const int64_t st = alloc_stagger();
+    if (st == 0) return cudaMalloc(dptr, nbytes);
+    void *base = nullptr;
+    const cudaError_t e = cudaMalloc(&base, nbytes + (size_t)st * 32);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(g_alloc_mu);
+    void *p = (char *)base + (size_t)st * (g_alloc_count++ % 32u);
+    g_alloc_base[p] = base;
+    *dptr = p;
+    return cudaSuccess;
+}
+cudaError_t staggered_free(void *dptr)
+{
+    if (!dptr) return cudaSuccess;
+    void *base = dptr;
+    {
+        std::lock_guard<std::mutex> lk(g_alloc_mu);
+        auto it = g_alloc_base.find(dptr);
+        if (it != g_alloc_base.end()) {
+            base = it->second;
+            g_alloc_base.erase(it);
+        }
+    }
+    return cudaFree(base);
+}
+}  // namespace fc
+
 extern "C" int fc_device_malloc(int device, int64_t nbytes, void **dptr)
 {
     if (!dptr || nbytes < 0) return fail(nullptr, FC_ERR_ARG, "fc_device_malloc: bad argument");
     CUDA_TRY(nullptr, cudaSetDevice(device));
-    CUDA_TRY(nullptr, cudaMalloc(dptr, (size_t)std::max<int64_t>(nbytes, 8)));
+    CUDA_TRY(nullptr, staggered_malloc(dptr, (size_t)std::max<int64_t>(nbytes, 8)));
     return FC_OK;
 }
 extern "C" int fc_device_free(int device, void *dptr)
 {
     CUDA_TRY(nullptr, cudaSetDevice(device));
-    CUDA_TRY(nullptr, cudaFree(dptr));
+    CUDA_TRY(nullptr, staggered_free(dptr));
     return FC_OK;
 }
 extern "C" int fc_host_malloc_pinned(int64_t nbytes, void **hptr)
@@ -278,14 +329,14 @@ extern "C" int fc_destroy(fc_context *c)
     nccl_destroy(c);
     for (auto &b : c->bufs) {
         if (b.registered) cudaHostUnregister(b.user);
-        if (!b.user_is_device && b.dev) cudaFree(b.dev);
+        if (!b.user_is_device && b.dev) staggered_free(b.dev);
     }
     cudaFree(c->corr_dev);
     for (int g = 1; g <= 3; ++g)
         if (c->area_owned[g]) cudaFree(c->area_dev[g]);
     cudaFree(c->diag_partials);
-    cudaFree(c->diag_counter);
     cudaFree(c->diag_chunk_out);
+    cudaFree(c->tile_ctr);
     p2p_destroy(c);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->diag_buf[b]);
@@ -312,7 +363,7 @@ static void release_buffer(fc_context *c, int b)
     Buffer &B = c->bufs[b];
     if (--B.refs > 0) return;
     if (B.registered) cudaHostUnregister(B.user);
-    if (!B.user_is_device && B.dev) cudaFree(B.dev);
+    if (!B.user_is_device && B.dev) staggered_free(B.dev);
     B = Buffer();   // tombstone (indices of other buffers stay valid)
 }
 
@@ -347,7 +398,7 @@ extern "C" int fc_bind_field(fc_context *c, int i, int g, int idx, double *p, in
     if (B.user_is_device) {
         B.dev = p;
     } else {
-        CUDA_TRY(c, cudaMalloc(&B.dev, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
+        CUDA_TRY(c, staggered_malloc((void **)&B.dev, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
         if (c->pin_host && !B.user_is_pinned && n > 0) {
             if (cudaHostRegister(p, (size_t)n * sizeof(double), cudaHostRegisterPortable) == cudaSuccess) B.registered = true;
             else cudaGetLastError();
@@ -473,6 +524,11 @@ extern "C" int fc_set_option(fc_context *c, const char *name, int64_t value)
     else if (!strcmp(name, "h2d_chunks")) c->h2d_chunks = (int)std::max<int64_t>(0, std::min<int64_t>(value, 256));
     else if (!strcmp(name, "diagnostics")) c->diagnostics = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(name, "staged")) c->use_staged = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
+    else if (!strcmp(name, "early_loads")) c->early_loads = value != 0;
+    else if (!strcmp(name, "stream_touched")) {      // the caller enqueued own work on fc_get_stream(): no shortcut across it
+        c->tail_own_step = false;
+        return FC_OK;
+    }
     else if (!strcmp(name, "prefetch_distance")) c->prefetch_distance = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));
     else if (!strcmp(name, "profile_kernel")) {
         c->profile_kernel = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 20));   // 0 off, n: every n-th launch
@@ -491,6 +547,7 @@ extern "C" int fc_synchronize(fc_context *c)
 {
     if (!c) return fail(nullptr, FC_ERR_ARG, "NULL context");
     cudaSetDevice(c->device);
+    if (int rc = flush_fold(c)) return rc;      // the last step's diagnostics rows -> its result vector (and the peers' mailboxes)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (c->comm_stream) CUDA_TRY(c, cudaStreamSynchronize(c->comm_stream));
     return FC_OK;
@@ -835,6 +892,7 @@ static int run_ops(fc_context *c, const std::vector<HOp> &ops)
 {
     if (ops.empty()) return FC_OK;
     cudaSetDevice(c->device);
+    c->tail_own_step = false;
     // host-pointer mode: upload every buffer that is read before it is written, download what is written
     std::vector<int> up, down;
     {
@@ -1158,6 +1216,8 @@ static bool build_fused(fc_context *c, bool do_early, bool do_normal, FusedBundl
 static int prepare_impl(fc_context *c, int strict)
 {
     cudaSetDevice(c->device);
+    if (int rc = flush_fold(c)) return rc;
+    c->tail_own_step = false;
     c->strict = strict != 0;
     // validation == generating the full pass sequence once (reports what is lacking)
     {
@@ -1298,8 +1358,11 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P, int K)
     for (int k = 0; k < K; ++k) rows = std::max(rows, fused_diag_rows(chunk_plan(c, P, k, K)));
     const int planes = P.diag >= 2 ? 3 : 1;
     const size_t stride = (size_t)planes * P.diag_n * (size_t)rows + (size_t)diag_tmp_doubles(rows, P.diag_n);
-    const size_t need = stride * sizeof(double) * (size_t)K;
+    // K = 1: two sets, alternating by step -- the rows of step k are folded while step k + 1 writes its own (DiagFold)
+    const size_t need = stride * sizeof(double) * (size_t)std::max(K, 2);
     if (need > c->diag_partials_cap) {
+        if (int rc = flush_fold(c)) return rc;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->diag_partials);
         c->diag_partials = nullptr;
         CUDA_TRY(c, cudaMalloc(&c->diag_partials, need));
@@ -1313,15 +1376,12 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P, int K)
             CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_comm[b], cudaEventDisableTiming));
         }
     if (!c->diag_host) CUDA_TRY(c, cudaHostAlloc(&c->diag_host, sizeof(double) * kDiagSlots * 3 * 2, cudaHostAllocDefault));
-    if (!c->diag_counter) {
-        CUDA_TRY(c, cudaMalloc(&c->diag_counter, sizeof(unsigned int) * kMaxChunks));
-        CUDA_TRY(c, cudaMemsetAsync(c->diag_counter, 0, sizeof(unsigned int) * kMaxChunks, c->stream));
+    if (!c->diag_chunk_out) {
         CUDA_TRY(c, cudaMalloc(&c->diag_chunk_out, sizeof(double) * kDiagSlots * 3 * kMaxChunks));
         CUDA_TRY(c, cudaMemsetAsync(c->diag_chunk_out, 0, sizeof(double) * kDiagSlots * 3 * kMaxChunks, c->stream));
     }
     P.diag_partials = c->diag_partials;
     P.diag_rows = rows;
-    P.diag_counter = c->diag_counter;
     // result buffer of this step; if its previous all-reduce is still in flight on the side stream, wait for it
     const int b = c->diag_cur ^ 1;
     if (c->comm_busy[b]) {
@@ -1337,7 +1397,6 @@ static void diag_chunk_view(const fc_context *c, const FusedPlan &P, int k, int 
 {
     Q.diag_partials = c->diag_partials + (size_t)k * c->diag_chunk_stride;
     Q.diag_rows = P.diag_rows;
-    Q.diag_counter = c->diag_counter + k;
     Q.diag_out = (K == 1) ? P.diag_out : c->diag_chunk_out + (size_t)k * 3 * kDiagSlots;
 }
 
@@ -1357,6 +1416,35 @@ static int finalize_chunk(fc_context *c, const FusedPlan &Q, cudaStream_t s)
     return FC_OK;
 }
 
+// the rows a specialised launch of Q leaves behind, as a fold request
+static DiagFold make_fold(const FusedPlan &Q)
+{
+    DiagFold f;
+    memset(&f, 0, sizeof f);
+    f.rows = Q.diag_partials;
+    f.row_stride = Q.diag_rows;
+    f.plane = (int64_t)Q.diag_n * Q.diag_rows;
+    f.nrows = (int)fused_diag_rows(Q);
+    f.nslots = Q.diag_n;
+    f.level = Q.diag;
+    f.out = Q.diag_out;
+    return f;
+}
+
+namespace fc {
+// fold the rows of the last specialised step now (stand-alone kernel) if no later step has done it yet
+int flush_fold(fc_context *c)
+{
+    if (!c->fold_pending) return FC_OK;
+    cudaSetDevice(c->device);
+    if (launch_diag_fold(c->fold, c->stream)) return fail(c, FC_ERR_CUDA, "diag fold launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    c->launches += 1;
+    c->fold_pending = false;
+    c->tail_own_step = false;
+    return FC_OK;
+}
+}  // namespace fc
+
 // bookkeeping once the step's result vector (P.diag_out = diag_buf[next]) is issued
 static void diag_step_done(fc_context *c, const FusedPlan &P, const FusedBundle &F)
 {
@@ -1365,6 +1453,21 @@ static void diag_step_done(fc_context *c, const FusedPlan &P, const FusedBundle 
     c->diag_valid = false;
     c->diag_global = false;
     c->diag_level = P.diag;
+}
+
+// dynamic schedule: give launch Q claim counter `slot`; returns by how much the launch will advance it
+static int attach_tile_counter(fc_context *c, FusedPlan &Q, int slot, unsigned int *claims)
+{
+    *claims = fused_dyn_claims(Q);
+    if (*claims == 0) return FC_OK;
+    if (!c->tile_ctr) {
+        CUDA_TRY(c, cudaMalloc(&c->tile_ctr, sizeof(unsigned int) * (kMaxChunks + 2)));
+        CUDA_TRY(c, cudaMemset(c->tile_ctr, 0, sizeof(unsigned int) * (kMaxChunks + 2)));
+        memset(c->tile_base, 0, sizeof c->tile_base);
+    }
+    Q.tile_counter = c->tile_ctr + slot;
+    Q.tile_base = c->tile_base[slot];
+    return FC_OK;
 }
 
 static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
@@ -1383,11 +1486,25 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     int nlaunch = 0;
 
     if (!any_host) {
+        const bool spec = fused_uses_spec(P) != 0;
+        // rows of the previous specialised step that nobody folded yet: this launch folds them while its ring fills,
+        // unless it is not that kind of launch
+        if (c->fold_pending && !(spec && P.diag))
+            if (int rc = flush_fold(c)) return rc;
         if (P.diag) {
             if (int rc = ensure_diag_storage(c, P, 1)) return rc;
-            diag_chunk_view(c, P, 0, 1, P);
-            p2p_next_post(c, P.post);      // peers connected: the kernel's last CTA posts the result to every rank
+            diag_chunk_view(c, P, c->row_set ^= 1, 1, P);
+            if (c->fold_pending) P.fold_prev = c->fold;
         }
+        P.early_loads = (spec && c->tail_own_step && c->early_loads) ? 1 : 0;
+        // dynamic schedule: consecutive steps alternate between two counters, because the producers of a step may claim
+        // while the previous step still runs.  That holds for at most two steps at a time only if this step's grid
+        // fills the device (a third step finds no room before the first has left); smaller grids wait first.
+        unsigned int claims = 0;
+        const int tslot = kMaxChunks + (c->tile_par ^= 1);
+        if (spec)
+            if (int rc = attach_tile_counter(c, P, tslot, &claims)) return rc;
+        if (claims && !fused_fills_device(P)) P.early_loads = 0;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->profile_kernel && c->prof_used < 8192 && (c->prof_seq++ % c->profile_kernel) == 0) {
             while (c->prof_ev.size() < c->prof_used + 2) {
@@ -1403,11 +1520,15 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         if (launch_fused(P, c->stream, &nlaunch)) return fail(c, FC_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (e1) CUDA_TRY(c, cudaEventRecord(e1, c->stream));
         c->launches += nlaunch;
+        c->tile_base[tslot] += claims;
+        c->fold_pending = false;      // (the launch took the previous step's rows along)
+        c->tail_own_step = spec;
         if (P.diag) {
-            if (int rc = finalize_chunk(c, P, c->stream)) return rc;
-            if (P.post.nranks > 1 && !fused_uses_spec(P)) {      // generic kernel: post with a small kernel
-                if (launch_diag_post(P.diag_out, P.post, (int)F.diag_slots.size(), c->stream)) return fail(c, FC_ERR_CUDA, "diag post launch failed");
-                c->launches += 1;
+            if (spec) {
+                c->fold = make_fold(P);
+                c->fold_pending = true;
+            } else if (int rc = finalize_chunk(c, P, c->stream)) {
+                return rc;
             }
             diag_step_done(c, P, F);
         }
@@ -1421,8 +1542,10 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     int64_t nmax = std::max(c->n[1], std::max(c->n[2], c->n[3]));
     const int K = c->h2d_chunks > 0 ? std::min(c->h2d_chunks, kMaxChunks)
                                     : (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(1, nmax / 262144));
+    if (int rc = flush_fold(c)) return rc;
     if (P.diag)
         if (int rc = ensure_diag_storage(c, P, K)) return rc;
+    c->tail_own_step = false;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (int k = 0; k < K; ++k) {
         cudaStream_t s = c->pipe[k % 3];
@@ -1438,9 +1561,18 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         }
         FusedPlan Q = chunk_plan(c, P, k, K);
         if (P.diag) diag_chunk_view(c, P, k, K, Q);
+        unsigned int claims = 0;
+        if (int rc = attach_tile_counter(c, Q, k, &claims)) return rc;
+        c->tile_base[k] += claims;
         if (launch_fused(Q, s, &nlaunch)) return fail(c, FC_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (P.diag)
-            if (int rc = finalize_chunk(c, Q, s)) return rc;
+        if (P.diag) {
+            if (fused_uses_spec(Q)) {      // the chunk's rows -> the chunk's result vector, right behind it on its stream
+                if (launch_diag_fold(make_fold(Q), s)) return fail(c, FC_ERR_CUDA, "diag fold launch failed");
+                nlaunch += 1;
+            } else if (int rc = finalize_chunk(c, Q, s)) {
+                return rc;
+            }
+        }
         for (int b : F.out_bufs) {
             const Buffer &B = c->bufs[b];
             if (B.user_is_device) continue;
@@ -1455,12 +1587,6 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     if (P.diag) {
         if (K > 1) {      // fold the chunks' result vectors in chunk order
             if (launch_diag_combine(c->diag_chunk_out, K, P.diag_out, c->stream)) return fail(c, FC_ERR_CUDA, "diag combine launch failed");
-            c->launches += 1;
-        }
-        if (c->p2p) {
-            PeerPost post;
-            p2p_next_post(c, post);
-            if (launch_diag_post(P.diag_out, post, (int)F.diag_slots.size(), c->stream)) return fail(c, FC_ERR_CUDA, "diag post launch failed");
             c->launches += 1;
         }
         diag_step_done(c, P, F);
@@ -1608,6 +1734,7 @@ int diag_fetch(fc_context *c)
     if (c->diag_valid) return FC_OK;
     if (c->diag_active.empty()) return fail(c, FC_ERR_STATE, "no diagnostics available: enable option 'diagnostics' and run a step");
     cudaSetDevice(c->device);
+    if (int rc = flush_fold(c)) return rc;
     const int b = c->diag_cur;
     if (c->comm_busy[b]) {      // the all-reduce of this buffer runs on the side stream
         CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_comm[b], 0));
@@ -1644,13 +1771,27 @@ extern "C" int fc_allreduce_diagnostics(fc_context *c)
 {
     if (!c) return fail(nullptr, FC_ERR_ARG, "NULL context");
     if (c->diag_active.empty()) return fail(c, FC_ERR_STATE, "no diagnostics to reduce");
-    if (c->p2p) {      // the step's kernel already posted the vector to every rank: nothing to launch
+    if (c->p2p) {
+        // one more exchange: its record goes into every rank's mailbox together with the fold of the step's rows -- by the
+        // next step's kernel, or by fc_get_diagnostics / fc_synchronize, whichever comes first -- or right now if the
+        // result vector is already complete (generic kernels, host-pointer pipeline)
+        PeerPost post;
+        p2p_make_post(c, post);
+        if (c->fold_pending) {
+            c->fold.post = post;
+        } else {
+            cudaSetDevice(c->device);
+            if (launch_diag_post(c->diag_buf[c->diag_cur], post, (int)c->diag_active.size(), c->stream)) return fail(c, FC_ERR_CUDA, "diag post launch failed");
+            c->launches += 1;
+            c->tail_own_step = false;
+        }
         c->diag_valid = false;
         c->diag_global = true;
         return FC_OK;
     }
     if (c->nranks <= 1 || !c->nccl_comm) return FC_OK;   // single rank: local == global
     c->diag_valid = false;
+    if (int rc = flush_fold(c)) return rc;
     return nccl_allreduce_diag(c);
 }
 
@@ -1709,6 +1850,7 @@ extern "C" int fc_regrid(fc_context *c, int dir, double *dst, const double *src)
     RegridMatrix &M = c->regrid[dir];
     if (!M.set) return fail(c, FC_ERR_STATE, "fc_regrid: matrix %d not set", dir);
     cudaSetDevice(c->device);
+    c->tail_own_step = false;
     bool sd, sp, dd, dp;
     classify_pointer(src, &sd, &sp, nullptr);
     classify_pointer(dst, &dd, &dp, nullptr);

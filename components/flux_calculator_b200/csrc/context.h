@@ -66,6 +66,9 @@ extern thread_local std::string g_last_error;
 int fail(fc_context *ctx, int code, const char *fmt, ...);
 int classify_pointer(const void *p, bool *is_device, bool *is_pinned, int *device);
 int diag_fetch(fc_context *c);
+int flush_fold(fc_context *c);
+cudaError_t staggered_malloc(void **dptr, size_t nbytes);
+cudaError_t staggered_free(void *dptr);
 
 }  // namespace fc
 
@@ -118,7 +121,17 @@ struct fc_context {
     // diagnostics storage
     double *diag_partials = nullptr;
     size_t diag_partials_cap = 0;
-    unsigned int *diag_counter = nullptr;   // last-CTA-done counters of the specialised kernel, one per chunk
+    fc::DiagFold fold;                      // rows of the last specialised step (device-resident path), not folded yet
+    bool fold_pending = false;
+    int row_set = 0;                        // which of the two row sets the last device-resident step wrote
+    bool tail_own_step = false;             // the last operation enqueued on `stream` is a specialised step kernel
+    bool early_loads = true;                // option: let such a step's successor fill its ring before griddepcontrol.wait
+    // dynamic tile schedule (specialised kernel without diagnostics): monotonic claim counters, one per chunk of the host
+    // pipeline plus two that alternate between consecutive device-resident steps (a step's producers may start claiming
+    // while the previous step still runs); tile_base = what each counter will read before its next launch
+    unsigned int *tile_ctr = nullptr;
+    unsigned int tile_base[fc::kMaxChunks + 2] = {};
+    int tile_par = 0;
     double *diag_chunk_out = nullptr;       // [kMaxChunks][sum|min|max][kDiagSlots]: per-chunk results (host-pointer pipeline)
     size_t diag_chunk_stride = 0;           // doubles of partial rows + reduce scratch per chunk
     double *diag_buf[2] = {nullptr, nullptr};   // [sum|min|max][kDiagSlots] compact slots, double buffered by step
@@ -135,10 +148,10 @@ struct fc_context {
     void *nccl_comm = nullptr;
     int rank = 0, nranks = 1;
     // peer-memory exchange (p2p_comm.cu)
-    fc::DiagMail *mailbox = nullptr;           // own mailbox [2][kMaxPeers slots, nranks used]
+    fc::DiagMail *mailbox = nullptr;           // own mailbox [kMailDepth][nranks]
     fc::DiagMail *peer_mail[fc::kMaxPeers] = {};   // every rank's mailbox as mapped here (peer_mail[rank] == mailbox)
     bool p2p = false;                          // connected
-    unsigned long long diag_seq = 0;           // sequence number of the last step that produced diagnostics
+    unsigned long long diag_seq = 0;           // number of exchanges so far (fc_allreduce_diagnostics calls, a collective)
     bool diag_global = false;                  // fc_allreduce_diagnostics was called for the last step
 
     fc::RegridMatrix regrid[4];

@@ -798,6 +798,18 @@ static FusedGeom fused_geometry(const FusedPlan &p)
 // 1: the main part of this plan runs on the specialised persistent kernel, 0: on the generic fused kernel
 int fused_uses_spec(const FusedPlan &p) { return fused_geometry(p).spec ? 1 : 0; }
 
+int fused_fills_device(const FusedPlan &p)
+{
+    const FusedGeom G = fused_geometry(p);
+    return (G.spec && G.spec_grid >= spec_capacity(p.S)) ? 1 : 0;
+}
+
+unsigned int fused_dyn_claims(const FusedPlan &p)
+{
+    const FusedGeom G = fused_geometry(p);
+    return G.spec ? spec_dyn_claims(p, G.spec_first, G.spec_cells) : 0u;
+}
+
 int64_t fused_diag_rows(const FusedPlan &p)
 {
     const FusedGeom G = fused_geometry(p);
@@ -849,7 +861,7 @@ int launch_diag_finalize(const FusedPlan &p, double *tmp, double *diag_out, cuda
 {
     if (!p.diag || p.diag_n <= 0) return 0;
     const FusedGeom G = fused_geometry(p);
-    if (G.spec && G.diag_accum) return 0;      // reduced in-kernel by the last CTA, diag_out is already written
+    if (G.spec && G.diag_accum) return 0;      // one row per CTA, folded later (DiagFold): the caller keeps track
     const int w = kFusedThreads / 32;
     DiagRanges R;
     memset(&R, 0, sizeof R);
@@ -903,7 +915,7 @@ __global__ void diag_post_kernel(const double *__restrict__ diag_out, const __gr
     unsigned long long w[3][2];
     for (int pl = 0; pl < 3; ++pl) diag_mail_pack(diag_out[pl * kDiagSlots + t], (unsigned int)post.seq, w[pl]);
     for (int r = 0; r < post.nranks; ++r) {
-        DiagMail *m = post.mail[r] + (size_t)post.parity * post.nranks + post.rank;
+        DiagMail *m = post.mail[r] + (size_t)post.slot * post.nranks + post.rank;
         for (int pl = 0; pl < 3; ++pl) {
             __stcg(&m->w[pl][t][0], w[pl][0]);
             __stcg(&m->w[pl][t][1], w[pl][1]);

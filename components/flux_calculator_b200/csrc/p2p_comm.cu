@@ -9,8 +9,12 @@
 // rank order on the host, so all ranks see bit-identical global sums.  NCCL (nccl_dyn.cu) remains as the fallback
 // when IPC is unavailable.
 //
-// Double buffering: a record of step k is overwritten by step k+2; a reader that comes later than that gets an
-// error, never mixed data (every word carries its step's tag).
+// Records are keyed by EXCHANGE, not by step: fc_allreduce_diagnostics (a collective: every rank calls it for the same
+// steps) numbers the exchanges, and the record of exchange e lives in slot e mod kMailDepth of every mailbox.  Steps
+// whose global values nobody asked for post nothing.  Ranks that all read every exchange keep each other in lock step
+// (a reader waits for every rank's record of e before it can start e + 1), so a slot is never reused under a reader;
+// a rank that does not read may run at most kMailDepth - 1 exchanges ahead of one that does -- beyond that the late
+// reader gets an error, never mixed data (every word carries its exchange's tag).
 #include "context.h"
 
 #include <string.h>
@@ -27,7 +31,7 @@ extern "C" int fc_comm_p2p_handle(fc_context *c, char handle[FC_P2P_HANDLE_BYTES
     if (!c || !handle) return fail(c, FC_ERR_ARG, "fc_comm_p2p_handle: NULL argument");
     cudaSetDevice(c->device);
     if (!c->mailbox) {
-        const size_t bytes = sizeof(DiagMail) * 2 * kMaxPeers;
+        const size_t bytes = sizeof(DiagMail) * kMailDepth * kMaxPeers;
         CUDA_TRY(c, cudaMalloc(&c->mailbox, bytes));
         CUDA_TRY(c, cudaMemset(c->mailbox, 0, bytes));
     }
@@ -81,8 +85,8 @@ void p2p_destroy(fc_context *c)
     c->p2p = false;
 }
 
-// the PeerPost block of the step about to be issued
-void p2p_next_post(fc_context *c, PeerPost &post)
+// the PeerPost block of the next exchange
+void p2p_make_post(fc_context *c, PeerPost &post)
 {
     memset(&post, 0, sizeof post);
     if (!c->p2p) return;
@@ -90,17 +94,17 @@ void p2p_next_post(fc_context *c, PeerPost &post)
     post.nranks = c->nranks;
     post.rank = c->rank;
     post.seq = c->diag_seq;
-    post.parity = (int)(c->diag_seq & 1ull);
+    post.slot = (int)(c->diag_seq % (unsigned long long)kMailDepth);
     for (int r = 0; r < c->nranks; ++r) post.mail[r] = c->peer_mail[r];
 }
 
 // global diagnostics of the last step: wait until every needed word of every rank carries that step's tag, fold in rank order
 int p2p_fetch(fc_context *c, double *planes /* [3][kDiagSlots] */, int n_active, int level)
 {
-    const int R = c->nranks, parity = (int)(c->diag_seq & 1ull);
+    const int R = c->nranks, slot = (int)(c->diag_seq % (unsigned long long)kMailDepth);
     const unsigned int want = (unsigned int)c->diag_seq;
     std::vector<DiagMail> host((size_t)R);
-    const DiagMail *src = c->mailbox + (size_t)parity * R;
+    const DiagMail *src = c->mailbox + (size_t)slot * R;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));      // our own record is posted
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
@@ -113,14 +117,15 @@ int p2p_fetch(fc_context *c, double *planes /* [3][kDiagSlots] */, int n_active,
                         const unsigned int tag = (unsigned int)(host[r].w[pl][k][h] >> 32);
                         if (tag == want) continue;
                         if ((int)(tag - want) > 0)
-                            return fail(c, FC_ERR_STATE, "diagnostics of step %llu were overwritten: rank %d is already %d step(s) further "
-                                        "(read the global diagnostics at most one step late)", c->diag_seq, r, (int)(tag - want));
+                            return fail(c, FC_ERR_STATE, "diagnostics of exchange %llu were overwritten: rank %d is already %d exchange(s) "
+                                        "further (a rank that does not read may run at most %d exchanges ahead of one that does)",
+                                        c->diag_seq, r, (int)(tag - want), kMailDepth - 1);
                         all = false;      // not arrived yet
                         break;
                     }
         if (all) break;
         if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 30.0)
-            return fail(c, FC_ERR_NCCL, "peer diagnostics of step %llu did not arrive within 30 s", c->diag_seq);
+            return fail(c, FC_ERR_NCCL, "peer diagnostics of exchange %llu did not arrive within 30 s (every rank must call fc_allreduce_diagnostics for it and then issue another step, read or synchronize)", c->diag_seq);
         usleep(20);
     }
     // every word of this snapshot validated itself: fold

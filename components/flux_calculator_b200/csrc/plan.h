@@ -126,11 +126,26 @@ __host__ __device__ inline void diag_mail_pack(double x, unsigned int seq32, uns
     out[0] = ((unsigned long long)seq32 << 32) | (b & 0xffffffffull);
     out[1] = ((unsigned long long)seq32 << 32) | (b >> 32);
 }
+constexpr int kMailDepth = 8;       // mailbox records per source rank: the record of exchange e lives in slot e mod kMailDepth
 struct PeerPost {
     int nranks, rank;                // nranks <= 1: off
-    int parity, pad;
-    unsigned long long seq;
+    int slot, pad;                   // seq mod kMailDepth
+    unsigned long long seq;          // number of the exchange (fc_allreduce_diagnostics calls so far), the words' tag
     DiagMail *mail[kMaxPeers];       // mailbox base of every rank (the own one included), mapped into this process
+};
+
+// Rows of a specialised launch (one per CTA) that still have to be folded into that step's result vector.  The
+// specialised kernel does not fold its own rows: the CTAs just leave their row and exit, and the fold runs where it
+// costs nothing -- in the producer warps of the NEXT step's kernel while its ring fills (griddepcontrol.wait orders
+// it after the rows) -- or in a one-warp-per-slot kernel when the host asks for the values first.  Same function,
+// same order, same bits either way.
+struct DiagFold {
+    const double *rows;              // [plane][compact slot][row_stride]
+    int64_t row_stride, plane;       // plane = nslots * row_stride
+    int nrows, nslots;               // rows written per slot (= grid of that launch); nslots == 0: nothing to fold
+    int level, pad;                  // 1: sums, 2: sums + min/max
+    double *out;                     // [sum|min|max][kDiagSlots]
+    PeerPost post;                   // nranks > 1: also post the result to every rank's mailbox
 };
 
 struct FusedPlan {
@@ -143,9 +158,12 @@ struct FusedPlan {
     Consts c;
     FusedT t;
     FusedUV uv[2];           // [0] = u grid, [1] = v grid
-    PeerPost post;           // in-kernel peer exchange of the result vector (specialised kernel, device-resident step)
-    double *diag_out;        // [sum|min|max][kDiagSlots] result of this step (written in-kernel by the specialised kernel)
-    unsigned int *diag_counter;   // CTAs done (last-CTA reduction of the specialised kernel); zero between launches
+    DiagFold fold_prev;      // rows of the previous specialised launch of the stream, folded by this launch (nslots == 0: none)
+    int early_loads;         // the previous operation of the stream is this library's own step kernel (which writes no
+                             // input): the producers may start their first bulk copies before griddepcontrol.wait
+    unsigned int tile_base;  // dynamic tile schedule of the specialised kernel without diagnostics: the counter's value
+    unsigned int *tile_counter;   // before this launch (it is never reset, see spec_kernel.cu)
+    double *diag_out;        // [sum|min|max][kDiagSlots] result of this step
     double *diag_partials;   // [plane: sum|min|max][diag_n][diag_rows]
     int64_t diag_rows;       // warp rows of one fused step (row stride of the partials)
     int diag_n;              // number of active diagnostics slots
@@ -173,6 +191,7 @@ int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t st
 int launch_fused(const FusedPlan &plan, cudaStream_t stream, int *launches);
 int launch_diag_finalize(const FusedPlan &plan, double *tmp, double *diag_out, cudaStream_t stream, int *launches);
 int launch_diag_post(const double *diag_out, const PeerPost &post, int n_active, cudaStream_t stream);
+int launch_diag_fold(const DiagFold &fold, cudaStream_t stream);      // spec_kernel.cu: the stand-alone fold
 int launch_diag_combine(const double *chunk_out, int nchunks, double *diag_out, cudaStream_t stream);
 int64_t fused_diag_rows(const FusedPlan &plan);
 int fused_uses_spec(const FusedPlan &plan);
@@ -181,6 +200,10 @@ unsigned long long read_exact_calls();
 // specialised persistent kernel (spec_kernel.cu)
 int spec_applicable(const FusedPlan &plan, const int64_t first[3], const int64_t cells[3]);
 int spec_launch(const FusedPlan &plan, const int64_t first[3], const int64_t cells[3], cudaStream_t stream);
+unsigned int spec_dyn_claims(const FusedPlan &plan, const int64_t first[3], const int64_t cells[3]);
+int spec_capacity(int num_surface_types);
+int fused_fills_device(const FusedPlan &plan);      // the specialised launch of this plan occupies every CTA slot of the device
+unsigned int fused_dyn_claims(const FusedPlan &plan);      // kernels.cu: the same for a whole fused step (0: static schedule)
 unsigned long long read_spec_exact_calls();
 int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,

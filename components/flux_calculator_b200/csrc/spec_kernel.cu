@@ -15,9 +15,11 @@
 //   * formula set and number of surface types are template parameters -- no method dispatch inside the kernel;
 //     area-fraction averages over the surface types (average_across_surface_types) are formed in registers;
 //   * diagnostics: per-thread running sums (and min/max at level 2) over all tiles of a thread, one warp tree per
-//     quantity per kernel, the CTA's warps combined in shared memory into one row per CTA, and the LAST CTA to
-//     finish (atomic counter) folds all rows into the result vector and posts it to the peer GPUs' mailboxes over
-//     NVLink: no follow-up kernel, no collective launch.  Static schedule + fixed trees: reproducible sums;
+//     quantity per kernel, the CTA's warps combined in shared memory into one row per CTA -- and that is all a CTA
+//     does at its end: no fence, no atomic, no last-CTA reduction on the tail of the step.  The rows are folded
+//     into the step's result vector (and posted to the peer GPUs' mailboxes over NVLink) by the producer warps of
+//     the NEXT step's kernel while its ring fills, or by a one-warp-per-slot kernel when the host asks first
+//     (DiagFold, plan.h).  Static schedule + fixed trees: reproducible sums;
 //   * cells whose operands leave the range in which the lock-step division / sqrt / exp / log sequences are
 //     proven (vmath.cuh) are NOT handled inline: the warp notes the tile, and a cold, out-of-line epilogue
 //     recomputes those tiles with the IEEE routines from global memory and rebuilds the warp's diagnostics
@@ -25,7 +27,9 @@
 //   * the ragged remainder of a grid (cells mod 512) is one more tile of the schedule, taken by its CTA before
 //     the ring tiles with guarded global loads/stores -- same chain code, no second launch;
 //   * launched with programmatic stream serialisation: the next step's CTAs become resident and set up their
-//     barriers while this step drains, then wait (griddepcontrol.wait) before touching global memory.
+//     barriers while this step drains; consumers wait (griddepcontrol.wait) before touching global memory, and
+//     when the previous kernel of the stream is this library's own step (which writes no input array) the
+//     producer fills the ring BEFORE it waits, so the fill overlaps the previous step's tail.
 //
 // Everything else (S > 2, 'zero'/'none' mixes, averaged QSUR, misaligned arrays, early-only phase) runs on the
 // generic kernels of kernels.cu, instantiated from the same formula templates.
@@ -33,6 +37,7 @@
 
 #include <cuda_runtime.h>
 #include <float.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace fc {
@@ -48,13 +53,16 @@ constexpr int kSpecV = 2;
 #ifndef FC_SPEC2_TEAMS
 #define FC_SPEC2_TEAMS 2            // two surface types: 2 teams x 8 warps x 512-cell tiles, or 4 teams x 4 warps x 256-cell tiles
 #endif
+#ifndef FC_SPEC2_TEAM_WARPS
+#define FC_SPEC2_TEAM_WARPS (16 / FC_SPEC2_TEAMS)
+#endif
 #ifndef FC_SPEC_PAR_PRODUCER
 #define FC_SPEC_PAR_PRODUCER 0      // 0: lane 0 of the producer warp issues all bulk copies of a tile; 1: lane a issues slot a
 #endif
 template <int NS>
 struct SpecGeom {
     static constexpr int kTeams = (NS == 1) ? 1 : FC_SPEC2_TEAMS;
-    static constexpr int kTeamWarps = (NS == 1) ? 8 : 16 / FC_SPEC2_TEAMS;     // consumer warps of one team = one tile per pass
+    static constexpr int kTeamWarps = (NS == 1) ? 8 : FC_SPEC2_TEAM_WARPS;     // consumer warps of one team = one tile per pass
     static constexpr int kTeamThreads = kTeamWarps * 32;
     static constexpr int kTile = kTeamThreads * kSpecV;      // cells per tile
     static constexpr int kSlotBytes = kTile * 8;             // one array of one tile
@@ -120,9 +128,10 @@ struct SpecPlan {
     double *out[kSpecMaxNS + 1][DQ_COUNT];   // [surface type, 0 = average][quantity] (null: not produced)
     double *partials;                 // [plane][compact slot][row]; rows [0, grid) are this kernel's (one per CTA)
     int64_t rows, plane;
-    double *diag_out;                 // [sum|min|max][kDiagSlots]
-    unsigned int *counter;            // CTAs done
-    PeerPost post;                    // peer mailboxes (multi-GPU): the last CTA also posts the result there
+    DiagFold prev;                    // rows of the previous launch, folded here while the ring fills (nslots == 0: none)
+    int early_loads;                  // first bulk copies before griddepcontrol.wait (previous kernel = own step)
+    unsigned int tile_base;           // dynamic schedule: value of *tile_counter before this launch's first claim
+    unsigned int *tile_counter;       // dynamic schedule: tiles are claimed with atomicAdd (never reset: the host tracks the base)
     signed char dmap[(kSpecMaxNS + 1) * DQ_COUNT];   // type * DQ_COUNT + quantity -> compact diagnostics slot (-1: inactive)
 };
 
@@ -408,13 +417,76 @@ __device__ __forceinline__ void consumer_barrier()
     asm volatile("bar.sync 1, %0;" ::"n"(SpecGeom<NS>::kConsumers) : "memory");
 }
 
-// end of kernel, consumer warps only: warps -> one row per CTA -> (last CTA) rows of all CTAs -> result (+ peer mailboxes)
+// one warp folds the rows of compact slot cs into the result vector: lane-strided rows, then a tree -- a fixed order, the
+// same in the next step's kernel and in the stand-alone fold kernel -- and posts the result to the peers' mailboxes
+__device__ __forceinline__ void diag_fold_slot(const DiagFold &f, int cs)
+{
+    const int lane = threadIdx.x & 31;
+    const double *col = f.rows + (int64_t)cs * f.row_stride;
+    const bool mm = f.level >= 2;
+    double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
+    constexpr int kPer = 10;      // rows per lane fetched at once (2 CTAs x 148 SMs = 296 rows -> one round)
+    for (int r0 = 0; r0 < f.nrows; r0 += 32 * kPer) {
+        double vs[kPer], vn[kPer], vx[kPer];
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            const int r = r0 + k * 32 + lane;
+            vs[k] = (r < f.nrows) ? __ldcg(col + r) : 0.0;
+            vn[k] = (mm && r < f.nrows) ? __ldcg(col + f.plane + r) : DBL_MAX;
+            vx[k] = (mm && r < f.nrows) ? __ldcg(col + 2 * f.plane + r) : -DBL_MAX;
+        }
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            s = add(s, vs[k]);
+            mn = fmin(mn, vn[k]);
+            mx = fmax(mx, vx[k]);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s = add(s, __shfl_down_sync(0xffffffffu, s, off));
+        mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
+        mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
+    }
+    s = __shfl_sync(0xffffffffu, s, 0);
+    mn = __shfl_sync(0xffffffffu, mn, 0);
+    mx = __shfl_sync(0xffffffffu, mx, 0);
+    if (lane == 0) {
+        f.out[0 * kDiagSlots + cs] = s;
+        f.out[1 * kDiagSlots + cs] = mn;
+        f.out[2 * kDiagSlots + cs] = mx;
+    }
+    // compute -> exchange without a collective launch: the result goes straight into every rank's mailbox over NVLink
+    // as self-validating 8-byte words (no fence, no flag store: see DiagMail); one lane per (rank, plane)
+    if (f.post.nranks > 1) {
+        for (int e = lane; e < f.post.nranks * 3; e += 32) {
+            const int r = e / 3, pl = e - 3 * r;
+            unsigned long long w[2];
+            diag_mail_pack(pl == 0 ? s : (pl == 1 ? mn : mx), (unsigned int)f.post.seq, w);
+            DiagMail *m = f.post.mail[r] + (size_t)f.post.slot * f.post.nranks + f.post.rank;
+            __stcg(&m->w[pl][cs][0], w[0]);
+            __stcg(&m->w[pl][cs][1], w[1]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) diag_fold_kernel(const __grid_constant__ DiagFold f) { diag_fold_slot(f, (int)blockIdx.x); }
+
+int launch_diag_fold(const DiagFold &f, cudaStream_t stream)
+{
+    if (f.nslots <= 0) return 0;
+    diag_fold_kernel<<<f.nslots, 32, 0, stream>>>(f);
+    return (int)cudaGetLastError();
+}
+
+// end of kernel, consumer warps only: warps -> one row per CTA.  Nothing else: the rows are folded after this grid
+// completed (DiagFold), so neither a fence nor a counter is needed here.
 template <int NS, int DIAG>
-__device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums<NS, DIAG> &ws, int *is_last)
+__device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums<NS, DIAG> &ws)
 {
     constexpr int kWarps = WarpSums<NS, DIAG>::kWarps;
     constexpr int kSlots = WarpSums<NS, DIAG>::kSlots;
-    const int tid = threadIdx.x, G = gridDim.x;
+    const int tid = threadIdx.x;
     consumer_barrier<NS>();
     if (tid < kSlots) {
         const int cs = p.dmap[NS == 1 ? DQ_COUNT + tid : tid];      // one type: staging holds surface type 1
@@ -435,71 +507,7 @@ __device__ __forceinline__ void diag_finish(const SpecPlan &p, WarpSums<NS, DIAG
                 o[2 * p.plane] = mx;
             }
         }
-        __threadfence();
     }
-    consumer_barrier<NS>();
-    if (tid == 0) *is_last = (atomicAdd(p.counter, 1u) == (unsigned)(G - 1));
-    consumer_barrier<NS>();
-    if (!*is_last) return;
-    __threadfence();
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int q = warp; q < kSlots; q += kWarps) {      // one warp per quantity, fixed order: lane-strided rows, then a tree
-        const int cs = p.dmap[NS == 1 ? DQ_COUNT + q : q];
-        if (cs < 0) continue;
-        const double *col = p.partials + (int64_t)cs * p.rows;
-        double s = 0.0, mn = DBL_MAX, mx = -DBL_MAX;
-        constexpr int kPer = 10;      // rows per lane fetched at once (2 CTAs x 148 SMs = 296 rows -> one round)
-        for (int r0 = 0; r0 < G; r0 += 32 * kPer) {
-            double vs[kPer], vn[kPer], vx[kPer];
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                const int r = r0 + k * 32 + lane;
-                vs[k] = (r < G) ? __ldcg(col + r) : 0.0;
-                if (DIAG >= 2) {
-                    vn[k] = (r < G) ? __ldcg(col + p.plane + r) : DBL_MAX;
-                    vx[k] = (r < G) ? __ldcg(col + 2 * p.plane + r) : -DBL_MAX;
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < kPer; ++k) {
-                s = add(s, vs[k]);
-                if (DIAG >= 2) {
-                    mn = fmin(mn, vn[k]);
-                    mx = fmax(mx, vx[k]);
-                }
-            }
-        }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            s = add(s, __shfl_down_sync(0xffffffffu, s, off));
-            if (DIAG >= 2) {
-                mn = fmin(mn, __shfl_down_sync(0xffffffffu, mn, off));
-                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, off));
-            }
-        }
-        if (lane == 0) {
-            p.diag_out[0 * kDiagSlots + cs] = s;
-            p.diag_out[1 * kDiagSlots + cs] = mn;
-            p.diag_out[2 * kDiagSlots + cs] = mx;
-            // compute -> exchange in one kernel: the result goes straight into every rank's mailbox over NVLink, as
-            // self-validating 8-byte words (no fence, no flag store: see DiagMail)
-            if (p.post.nranks > 1) {
-                unsigned long long ws_[3][2];
-                diag_mail_pack(s, (unsigned int)p.post.seq, ws_[0]);
-                diag_mail_pack(mn, (unsigned int)p.post.seq, ws_[1]);
-                diag_mail_pack(mx, (unsigned int)p.post.seq, ws_[2]);
-                for (int r = 0; r < p.post.nranks; ++r) {
-                    DiagMail *m = p.post.mail[r] + (size_t)p.post.parity * p.post.nranks + p.post.rank;
-#pragma unroll
-                    for (int pl = 0; pl < 3; ++pl) {
-                        __stcg(&m->w[pl][cs][0], ws_[pl][0]);
-                        __stcg(&m->w[pl][cs][1], ws_[pl][1]);
-                    }
-                }
-            }
-        }
-    }
-    if (tid == 0) *p.counter = 0u;      // ready for the next launch (same stream)
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -675,6 +683,222 @@ __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t 
         }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// dynamic tile schedule (the instantiations without diagnostics)
+// ---------------------------------------------------------------------------------------------
+// With the static round-robin schedule every CTA owns the same number of tiles, but the SMs do not stream at the
+// same speed (ncu: sm__cycles_active min / avg / max = 0.68 / 0.84 / 1.0 of the kernel for the RCO set, 0.84 / 0.92 / 1.0
+// for CCLM without diagnostics): the step ends when the slowest SM ends, with DRAM far from saturated on the tail.
+// Without diagnostics nothing depends on WHICH CTA computes a tile, so the producers claim tiles one by one from a global
+// counter (atomicAdd; claims are monotonic per CTA, hence every CTA still sees t tiles first, then u, then v and the
+// two ring carvings need no change) and hand the tile number to the consumers through shared memory, published by
+// the same mbarrier phase that publishes the tile's bytes.  A phase ends with one sentinel per team.  Partial tiles
+// are claimed like all others and read straight from global memory.  The counter is never reset: every producer
+// makes exactly one failing claim, so a launch advances it by (tiles + CTAs) and the host keeps the base.
+// (With diagnostics the per-thread running sums need a reproducible tile -> thread map: static schedule.)
+#ifndef FC_SPEC_DYNAMIC
+#define FC_SPEC_DYNAMIC 1
+#endif
+constexpr int kDynPartial = 1 << 30;      // tile id flag: partial tile, nothing in the stage
+
+template <int SET, int NS>
+__device__ __noinline__ void spec_cold_dyn(const SpecPlan &p, int uv, const int *ids, int n, int ttid)
+{
+    using GEO = SpecGeom<NS>;
+    for (int e = 0; e < n; ++e) {
+        const int id = ids[e] & ~kDynPartial;
+        const int ph = uv ? 1 + (id & 1) : 0;
+        const int64_t tile = uv ? (id >> 1) : id;
+        spec_fix_pair<SET, NS>(p, ph, p.first[ph] + tile * GEO::kTile + ttid * kSpecV);
+    }
+}
+
+template <int SET, int NS>
+__device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring, uint64_t *fullT, uint64_t *emptyT, uint64_t *fullU,
+                                                  uint64_t *emptyU, int *tileT, int *tileU, int (*flagged)[kSpecBadCap], int *nflagged)
+{
+    using GEO = SpecGeom<NS>;
+    using L = Lay<SET, NS>;
+    constexpr int TEAMS = GEO::kTeams;
+    const int NT = p.t_stages, NUS = p.u_stages, LT = p.t_bars, LU = p.u_bars;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned nt0 = (unsigned)p.ntiles[0], nt1 = (unsigned)p.ntiles[1], nt2 = (unsigned)p.ntiles[2];
+    const unsigned total = nt0 + nt1 + nt2;
+    const bool partial[3] = {(p.end[0] - p.first[0]) % GEO::kTile != 0, (p.end[1] - p.first[1]) % GEO::kTile != 0,
+                             (p.end[2] - p.first[2]) % GEO::kTile != 0};
+
+    if (warp == GEO::kWarps) {
+        // ---------------- producer: one lane claims, publishes and fetches ----------------
+        if (lane != 0) return;
+        unsigned g = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+        int i = 0;
+        {   // t tiles: local tile i -> stage i mod NT, barrier i mod LT
+            int st = 0, bi = 0, pb = 0, puse = 0;
+            auto slot = [&]() {      // wait until local tile i - NT (and with it every earlier one) is released, i.e. stage and id slot are free
+                if (i >= NT) {
+                    mbar_wait(&emptyT[pb], puse & 1);
+                    if (++pb == LT) {
+                        pb = 0;
+                        ++puse;
+                    }
+                }
+            };
+            auto next = [&]() {
+                if (++st == NT) st = 0;
+                if (++bi == LT) bi = 0;
+                ++i;
+            };
+            while (g < nt0) {
+                slot();
+                const bool part = partial[0] && g == nt0 - 1;
+                tileT[bi] = part ? (int)(g | kDynPartial) : (int)g;
+                if (part) {
+                    mbar_arrive(&fullT[bi]);
+                } else {
+                    const int64_t cell = p.first[0] + (int64_t)g * GEO::kTile;
+                    mbar_expect_tx(&fullT[bi], p.tx_bytes[0]);
+                    char *dst = ring + (size_t)st * p.t_stage_bytes;
+#pragma unroll 1
+                    for (int a = 0; a < L::NT; ++a)
+                        if (p.src[0][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[0][a] + cell, GEO::kSlotBytes, &fullT[bi]);
+                }
+                next();
+                g = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+            }
+            const int ring0 = i;      // t tiles this CTA took
+            for (int t = 0; t < TEAMS; ++t) {      // end of the t phase, once per team
+                slot();
+                tileT[bi] = -1;
+                mbar_arrive(&fullT[bi]);
+                next();
+            }
+            i = ring0;
+        }
+        {   // u and v tiles: local tile k -> stage k mod NUS of the u/v carving, barrier k mod LU
+            const int ring0 = i;
+            int st = 0, bi = 0, pb = 0, puse = 0, k = 0;
+            auto slot = [&]() {
+                if (k >= NUS) {
+                    mbar_wait(&emptyU[pb], puse & 1);
+                    if (++pb == LU) {
+                        pb = 0;
+                        ++puse;
+                    }
+                } else {      // first use of these bytes as a u/v stage: the last t tile of every t stage they overlap must be done
+                    const int lo = (st * p.u_stage_bytes) / p.t_stage_bytes, hi = ((st + 1) * p.u_stage_bytes - 1) / p.t_stage_bytes;
+                    for (int s = lo; s <= hi && s < NT; ++s)
+                        if (ring0 > s) {
+                            const int last = s + ((ring0 - 1 - s) / NT) * NT;
+                            mbar_wait(&emptyT[last % LT], (last / LT) & 1);
+                        }
+                }
+            };
+            auto next = [&]() {
+                if (++st == NUS) st = 0;
+                if (++bi == LU) bi = 0;
+                ++k;
+            };
+            while (g < total) {
+                const int ph = g < nt0 + nt1 ? 1 : 2;
+                const unsigned tile = g - (ph == 1 ? nt0 : nt0 + nt1);
+                slot();
+                const bool part = partial[ph] && tile == (ph == 1 ? nt1 : nt2) - 1;
+                tileU[bi] = (int)((tile << 1) | (unsigned)(ph - 1)) | (part ? kDynPartial : 0);
+                if (part) {
+                    mbar_arrive(&fullU[bi]);
+                } else {
+                    const int64_t cell = p.first[ph] + (int64_t)tile * GEO::kTile;
+                    mbar_expect_tx(&fullU[bi], p.tx_bytes[ph]);
+                    char *dst = ring + (size_t)st * p.u_stage_bytes;
+#pragma unroll 1
+                    for (int a = 0; a < L::NUV; ++a)
+                        if (p.src[ph][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[ph][a] + cell, GEO::kSlotBytes, &fullU[bi]);
+                }
+                next();
+                g = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+            }
+            for (int t = 0; t < TEAMS; ++t) {      // end of the step, once per team
+                slot();
+                tileU[bi] = -1;
+                mbar_arrive(&fullU[bi]);
+                next();
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers: team t takes local tiles t, t + TEAMS, ... of each phase ----------------
+    const int team = (TEAMS == 1) ? 0 : warp / GEO::kTeamWarps;
+    const int ttid = threadIdx.x - team * GEO::kTeamThreads;
+    const int toff = ttid * (kSpecV * 8);
+    NoDiag nd;
+    auto note = [&](int id, int uv) {      // a cell left the proven range: remember the tile; a full list is worked off at once
+        if (lane == 0) {
+            const int n = nflagged[warp];
+            flagged[warp][n] = id;
+            nflagged[warp] = n + 1;
+        }
+        __syncwarp();
+        if (nflagged[warp] == kSpecBadCap) {
+            spec_cold_dyn<SET, NS>(p, uv, flagged[warp], kSpecBadCap, ttid);
+            __syncwarp();
+            if (lane == 0) nflagged[warp] = 0;
+            __syncwarp();
+        }
+    };
+#pragma unroll 1
+    for (int uv = 0; uv < 2; ++uv) {
+        uint64_t *full = uv ? fullU : fullT, *empty = uv ? emptyU : emptyT;
+        const int *ids = uv ? tileU : tileT;
+        const int NS_ = uv ? NUS : NT, LB = uv ? LU : LT, sbytes = uv ? p.u_stage_bytes : p.t_stage_bytes;
+        int s = team % NS_, bi = team % LB, use = team / LB;
+        for (;;) {
+            mbar_wait(&full[bi], use & 1);
+            const int id = ids[bi];
+            if (id < 0) break;
+            const int tid_ = id & ~kDynPartial;
+            const int north = uv ? (tid_ & 1) : 0, ph = uv ? 1 + north : 0;
+            const int64_t j = p.first[ph] + (int64_t)(uv ? (tid_ >> 1) : tid_) * GEO::kTile + ttid * kSpecV;
+            FastVec<kSpecV> m;
+            bool bad;
+            if (!(id & kDynPartial)) {
+                const LdStage<GEO::kSlotBytes> ld{ring + (size_t)s * sbytes + toff};
+                const StPair st{j};
+                if (uv) spec_uv_chain<SET, NS>(m, p, north, ld, st, nd);
+                else spec_t_chain<SET, NS>(m, p, ld, st, nd);
+                bad = m.bad();
+            } else {
+                const int64_t left = p.end[ph] - j;
+                const int nv = left >= 2 ? 2 : (left > 0 ? (int)left : 0);
+                const LdPairGuard ld{p.src[ph], j, nv};
+                const StPairGuard st{j, nv};
+                if (uv) spec_uv_chain<SET, NS>(m, p, north, ld, st, nd);
+                else spec_t_chain<SET, NS>(m, p, ld, st, nd);
+                bad = nv > 0 && m.bad();
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[bi]);
+            if (__any_sync(0xffffffffu, bad)) note(id, uv);
+            s += TEAMS;
+            while (s >= NS_) s -= NS_;
+            bi += TEAMS;
+            while (bi >= LB) {
+                bi -= LB;
+                ++use;
+            }
+        }
+        __syncwarp();
+        const int nf = nflagged[warp];
+        if (nf) {
+            spec_cold_dyn<SET, NS>(p, uv, flagged[warp], nf, ttid);
+            __syncwarp();
+            if (lane == 0) nflagged[warp] = 0;
+            __syncwarp();
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -690,9 +914,10 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     __shared__ uint64_t fullT[kSpecMaxBars], emptyT[kSpecMaxBars], fullU[kSpecMaxBars], emptyU[kSpecMaxBars];
     __shared__ int flagged[GEO::kWarps][kSpecBadCap];
     __shared__ int nflagged[GEO::kWarps];
+    constexpr bool DYN = (DIAG == 0) && FC_SPEC_DYNAMIC;
+    __shared__ int tileT[DYN ? kSpecMaxBars : 1], tileU[DYN ? kSpecMaxBars : 1];      // dynamic schedule: tile of each barrier slot
     __shared__ WarpSums<NS, DIAG> ws;
     __shared__ double wacc[(NS > 1 && DIAG) ? GEO::kWarps : 1][(NS > 1 && DIAG) ? (DIAG >= 2 ? 3 : 1) * kDiagAccMax : 1];
-    __shared__ int is_last;
 
     const int NT = p.t_stages, NUS = p.u_stages, LT = p.t_bars, LU = p.u_bars;
     if (threadIdx.x == 0) {
@@ -717,10 +942,17 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
         }
     }
     __syncthreads();
-    // programmatic dependent launch: everything above overlapped the previous kernel of the stream; from here on
-    // global memory is touched, so wait for that kernel to complete (no-op without the launch attribute)
+    // programmatic dependent launch: everything above overlapped the previous kernel of the stream.  From here on
+    // global memory is touched, so wait for that kernel to complete (no-op without the launch attribute) -- except for
+    // the producer warp when the host vouches that the previous kernel is this library's own step, which writes none
+    // of the arrays the producer reads: it fills the ring first and waits afterwards (before it folds that step's rows)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool early_producer = p.early_loads && (threadIdx.x >> 5) == GEO::kWarps;
+    if (!early_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if constexpr (DYN) {      // (its producer never has to wait: it reads input arrays and the tile counter only)
+        spec_dynamic_body<SET, NS>(p, ring, fullT, emptyT, fullU, emptyU, tileT, tileU, flagged, nflagged);
+        return;
+    }
 
     // static schedule: this CTA takes positions b, b+G, b+2G, ... of the tile list [t tiles | u tiles | v tiles]
     const int G = gridDim.x, b = blockIdx.x;
@@ -748,11 +980,21 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
 
     if (warp == GEO::kWarps) {
         // ---------------- producer warp: lane 0 waits, arms the barrier and issues the bulk copies ----------------
-        if (!FC_SPEC_PAR_PRODUCER && lane != 0) return;
         {   // t tiles: tile i -> stage i mod NT, barrier i mod LT
             int st = 0, bi = 0, use = 0;          // of tile i
             int pb = 0, puse = 0;                 // of tile i - NT, the previous tenant of the stage
-            for (int i = 0; i < ring0; ++i) {
+            const int nfill = ring0 < NT ? ring0 : NT;      // the first pass over the stages waits for nobody
+            for (int i = 0;; ++i) {
+                if (i == nfill) {
+                    // the ring is filling: now (a) honour the stream order if the fill ran ahead of it, (b) fold the previous
+                    // step's diagnostics rows -- CTA b takes compact slots b, b + G, ... with the whole warp -- and
+                    // (c) retire the lanes that issue nothing
+                    if (early_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
+                    __syncwarp();
+                    for (int cs = b; cs < p.prev.nslots; cs += G) diag_fold_slot(p.prev, cs);
+                    if (!FC_SPEC_PAR_PRODUCER && lane != 0) return;
+                }
+                if (i >= ring0) break;
                 if (i >= NT) {
                     if (lane == 0) mbar_wait(&emptyT[pb], puse & 1);
                     if (++pb == LT) {
@@ -768,7 +1010,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
                 if (FC_SPEC_PAR_PRODUCER) {
                     if (lane < Lay<SET, NS>::NT && p.src[0][lane])
                         bulk_g2s(dst + lane * GEO::kSlotBytes, p.src[0][lane] + cell, GEO::kSlotBytes, &fullT[bi]);
-                } else {
+                } else if (lane == 0) {
 #pragma unroll 1
                     for (int a = 0; a < Lay<SET, NS>::NT; ++a)
                         if (p.src[0][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[0][a] + cell, GEO::kSlotBytes, &fullT[bi]);
@@ -855,11 +1097,15 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
         }
         int s = team % NT, bi = team % LT, use = team / LT, mine = 0;
         int64_t j = jbase + (int64_t)team * jstride;
+        // the cell areas do not travel through the ring: each thread fetches its 16 bytes ONE TILE AHEAD, so that the
+        // load's latency hides behind the chain of the current tile instead of in front of it
+        double2 a_next = make_double2(0.0, 0.0);
+        if (DIAG && team < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
         for (int i = team; i < ring0; i += TEAMS, j += TEAMS * jstride, ++mine) {
             if (DIAG) {
-                const double2 a = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
-                dg.area.v[0] = a.x;
-                dg.area.v[1] = a.y;
+                dg.area.v[0] = a_next.x;
+                dg.area.v[1] = a_next.y;
+                if (i + TEAMS < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j + TEAMS * jstride));
             }
             mbar_wait(&fullT[bi], use & 1);
             FastVec<kSpecV> m;
@@ -928,11 +1174,13 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
             int h = (kbase + i0) % NUS, bi = (kbase + i0) % LU, use = (kbase + i0) / LU, mine = 0;
             const int64_t jfirst = jbase + (int64_t)i0 * jstride;
             int64_t j = jfirst;
+            double2 a_next = make_double2(0.0, 0.0);
+            if (DIAG && i0 < ring_ph) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
             for (int i = i0; i < ring_ph; i += TEAMS, j += TEAMS * jstride, ++mine) {
                 if (DIAG) {
-                    const double2 a = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
-                    dg.area.v[0] = a.x;
-                    dg.area.v[1] = a.y;
+                    dg.area.v[0] = a_next.x;
+                    dg.area.v[1] = a_next.y;
+                    if (i + TEAMS < ring_ph) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j + TEAMS * jstride));
                 }
                 mbar_wait(&fullU[bi], use & 1);
                 FastVec<kSpecV> m;
@@ -967,7 +1215,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
             }
         }
     }
-    if (DIAG) diag_finish<NS, DIAG>(p, ws, &is_last);
+    if (DIAG) diag_finish<NS, DIAG>(p, ws);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1160,20 +1408,25 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     sp.partials = p.diag_partials;
     sp.rows = p.diag_rows;
     sp.plane = (int64_t)p.diag_n * p.diag_rows;
-    sp.diag_out = p.diag_out;
-    sp.counter = p.diag_counter;
-    sp.post = p.post;
-    if (!p.diag || sp.post.nranks <= 1) sp.post.nranks = 0;
+    sp.prev = p.fold_prev;
+    sp.tile_counter = p.tile_counter;
+    sp.tile_base = p.tile_base;
+    sp.early_loads = p.early_loads;
     *set_out = set;
     return true;
 }
 
+static int SpecGeomCtas(int ns) { return ns == 1 ? SpecGeom<1>::kCtasPerSm : SpecGeom<2>::kCtasPerSm; }
+
 static int spec_grid(const SpecPlan &sp)
 {
     const int64_t total = (int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2];
-    const int cap = (sp.ns == 1 ? 2 : 1) * spec_num_sms();
+    const int cap = SpecGeomCtas(sp.ns) * spec_num_sms();
     return (int)(total < cap ? total : cap);
 }
+
+// CTAs of the specialised kernel the device holds at once
+int spec_capacity(int num_surface_types) { return SpecGeomCtas(num_surface_types) * spec_num_sms(); }
 
 // > 0: the plan fits the specialised kernel, value = its grid size (= diagnostics rows); 0: it does not
 int spec_applicable(const FusedPlan &p, const int64_t first[3], const int64_t cells[3])
@@ -1182,6 +1435,17 @@ int spec_applicable(const FusedPlan &p, const int64_t first[3], const int64_t ce
     int set = 0;
     if (cells[0] + cells[1] + cells[2] <= 0 || !spec_build(p, first, cells, sp, &set)) return 0;
     return spec_grid(sp);
+}
+
+// dynamic schedule: by how much a launch of this plan advances the tile counter (every tile is claimed once, every CTA's
+// producer makes one failing claim); 0: the plan runs on the static schedule
+unsigned int spec_dyn_claims(const FusedPlan &p, const int64_t first[3], const int64_t cells[3])
+{
+    if (!FC_SPEC_DYNAMIC || p.diag) return 0;
+    SpecPlan sp;
+    int set = 0;
+    if (cells[0] + cells[1] + cells[2] <= 0 || !spec_build(p, first, cells, sp, &set)) return 0;
+    return (unsigned int)(sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] + spec_grid(sp));
 }
 
 template <int SET, int NS, int DIAG>
@@ -1206,7 +1470,8 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const int no_pdl = getenv("FC_NO_PDL") ? atoi(getenv("FC_NO_PDL")) : 0;      // tuning aid
+    attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, flux_spec_kernel<SET, NS, DIAG>, sp);
@@ -1225,7 +1490,8 @@ int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[
     SpecPlan sp;
     int set = 0;
     if (!spec_build(p, first, cells, sp, &set)) return (int)cudaErrorInvalidValue;
-    if (sp.diag && (!sp.partials || !sp.diag_out || !sp.counter)) return (int)cudaErrorInvalidValue;
+    if (sp.diag && !sp.partials) return (int)cudaErrorInvalidValue;
+    if (!sp.diag && FC_SPEC_DYNAMIC && !sp.tile_counter) return (int)cudaErrorInvalidValue;
     const int grid = spec_grid(sp);
     cudaError_t e;
     if (set == SET_BULK) e = (sp.ns == 1) ? spec_launch_d<SET_BULK, 1>(sp, grid, stream) : spec_launch_d<SET_BULK, 2>(sp, grid, stream);

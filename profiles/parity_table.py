@@ -16,7 +16,7 @@ import components.flux_calculator_b200 as m  # noqa: E402
 from components.flux_calculator_b200 import DeviceArray  # noqa: E402
 from components.flux_calculator_b200.synthetic import Scenario  # noqa: E402
 from oracle_py import Oracle, ulp_diff  # noqa: E402
-from tolerances import RTOL, SCALE  # noqa: E402
+from tolerances import K_ULP, ULP, Scales  # noqa: E402
 
 N = 2_000_000
 print("| set | S | field | cells differing | max ulp | max abs err | max rel err | worst err / tolerance |")
@@ -34,11 +34,12 @@ for fset, S in (("CCLM", 1), ("MOM5", 1), ("RCO", 1), ("CCLM", 2)):
     assert fc.info("spec_kernel") == 1
     fc.step_all(0)
     fc.synchronize()
+    scales = Scales(sc.inputs, o_out, sc.methods, sc.S)
     for k in sorted(o_out):
         got = wrapped[id(g_out[k])].download()
         ref = o_out[k]
         err = np.abs(got - ref)
-        tol = RTOL * np.abs(ref) + RTOL * SCALE.get(k[2], 0.0)
+        tol = K_ULP * ULP * (np.abs(ref) + scales.of(k))      # per cell: tests/tolerances.py
         with np.errstate(divide="ignore", invalid="ignore"):
             rel = np.where(ref != 0, err / np.abs(ref), 0.0)
             frac = np.where(tol > 0, err / tol, np.where(err > 0, np.inf, 0.0))
