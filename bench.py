@@ -119,64 +119,89 @@ class ClockSampler:
                 "how": "NVML polled every ~10 ms during the timed region" if self.nv else "nvidia-smi polled during the timed region"}
 
 
+SENT = [(1, "MEVA"), (1, "HLAT"), (1, "HSEN"), (1, "RBBR"), (1, "RSDR"), (2, "UMOM"), (3, "VMOM")]      # (grid, flux): what goes to oasis_put
+
+
 def build_scenario(workload, offset_size=None, cells=None):
-    from components.flux_calculator_b200.synthetic import Scenario
+    """the workload's fields + the send list of the reference's configuration: the seven fluxes, per surface type (and their
+    area-fraction averages on surface type 0 when there are two types); QSUR is an intermediate, never sent"""
+    from synthetic import Scenario
     fset, n, S, bias, avg, diag, _ = WORKLOADS[workload]
     if cells is not None:
         n = cells
     off, size = offset_size if offset_size else (0, n)
-    return Scenario(fset, n=(size, size, size), S=S, bias=bias, averaging=avg, offset=(off, off, off))
+    sc = Scenario(fset, n=(size, size, size), S=S, bias=bias, averaging=avg, offset=(off, off, off))
+    for i in range(1, S + 1):
+        for g, name in SENT:
+            if (i, g, name) in sc.outputs and (i, g, name) not in sc.send:
+                sc.send.append((i, g, name))
+    return sc
 
 
-def native_oracle():
-    """rebuild the release-like oracle with -march=native for THIS host (falls back to the shipped x86-64-v3 build)"""
+def native_oracle(build="fast"):
+    """the oracle built for THIS host: 'fast' = -O3 -march=native -ffast-math (the reference's release flags, -O3 -fp-model fast=2
+    -xHost, build_hlrng.sh:26), 'parity' = -O2 -ffp-contract=off (its debug / -fp-model precise build, :23); falls back to
+    the shipped builds"""
     import ctypes as C
     from oracle_py import ORACLE_DIR
+    flags = {"fast": ["-O3", "-march=native", "-ffast-math"], "parity": ["-O2", "-march=native", "-ffp-contract=off"]}[build]
     out = os.path.join(ORACLE_DIR, "_native")
     try:
         os.makedirs(out, exist_ok=True)
-        so = os.path.join(out, "liboracle_fast.so")
-        subprocess.check_call(["gcc", "-std=c11", "-O3", "-march=native", "-ffast-math", "-fPIC", "-shared", "-o", so,
+        so = os.path.join(out, "liboracle_%s.so" % build)
+        subprocess.check_call(["gcc", "-std=c11"] + flags + ["-fPIC", "-shared", "-o", so,
                                os.path.join(ORACLE_DIR, "flux_oracle.c"), os.path.join(ORACLE_DIR, "cpu_baseline.c"),
                                "-lm", "-lpthread"], stderr=subprocess.DEVNULL)
         C.CDLL(so)
-        return so, "-O3 -march=native -ffast-math"
+        return so, " ".join(flags)
     except Exception:
-        return os.path.join(ORACLE_DIR, "liboracle_fast.so"), "-O3 -march=x86-64-v3 -ffast-math"
+        return (os.path.join(ORACLE_DIR, "liboracle_fast.so" if build == "fast" else "liboracle.so"),
+                "-O3 -march=x86-64-v3 -ffast-math" if build == "fast" else "-O2 -ffp-contract=off")
 
 
-def cpu_arm(workload, steps, warmup, sample_cells, threads=None):
-    """the reference's CPU path (oracle port in the reference's loop structure) on all host threads"""
+def cpu_arm(workload, steps, warmup, sample_cells=None, variants=True):
+    """the reference's CPU path: the oracle port in the reference's loop structure (one pass per quantity and surface
+    type, one scalar call per cell, corrections at stride 12), P ranks each owning a contiguous range (threads standing in
+    for the MPI-parallel flux_calculator instances), on the workload's FULL grid.  Headline: release-like build on all
+    host threads; beside it the parity build (what the golden files pin) and one rank."""
     import oracle_py
-    so, flags = native_oracle()
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    P = threads or ncores
     fset, n, S, bias, avg, diag, _ = WORKLOADS[workload]
-    cells = min(n, sample_cells)
+    cells = min(n, sample_cells) if sample_cells else n
     sc = build_scenario(workload, cells=cells)
-    ins, outs = sc.clone()
-    orc = oracle_py.Oracle(sc.n, sc.S, fast=True, lib_path=so)
-    sc.apply(orc, ins, outs)
-    for _ in range(max(1, min(warmup, 2))):
-        orc.run_ranks(P, 1, 600, 0)
-    times = []
-    for k in range(steps):
-        t0 = time.perf_counter()
-        orc.run_ranks(P, 1, 600, 600 * k)
-        times.append(time.perf_counter() - t0)
-    t = float(np.mean(times))
-    return {"value": cells / t, "unit": UNIT, "cores": P, "kind": "port",
-            "sample": "%d cells/grid x %d steps of workload %s, %d ranks (threads) each owning a contiguous range, gcc %s"
-                      % (cells, steps, workload, P, flags),
-            "ms_per_step": t * 1e3}
+
+    def timed(build, P, nsteps, nwarm):
+        so, flags = native_oracle(build)
+        ins, outs = sc.clone()
+        orc = oracle_py.Oracle(sc.n, sc.S, fast=(build == "fast"), lib_path=so)
+        sc.apply(orc, ins, outs)
+        for _ in range(nwarm):
+            orc.run_ranks(P, 1, 600, 0)
+        times = []
+        for k in range(nsteps):
+            t0 = time.perf_counter()
+            orc.run_ranks(P, 1, 600, 600 * k)
+            times.append(time.perf_counter() - t0)
+        t = float(np.mean(times))
+        return {"value": cells / t, "ms_per_step": t * 1e3, "ranks": P, "steps": nsteps, "build": "gcc " + flags}
+
+    head = timed("fast", ncores, max(steps, 1), max(1, min(warmup, 3)))
+    res = {"value": head["value"], "unit": UNIT, "cores": ncores, "kind": "port",
+           "sample": "%d cells/grid (%s) x %d steps of workload %s, %d ranks (threads) each owning a contiguous range, %s"
+                     % (cells, "the full grid" if cells == n else "a sample", head["steps"], workload, ncores, head["build"]),
+           "ms_per_step": head["ms_per_step"]}
+    if variants:
+        one = max(1, min(3, steps))
+        res["variants"] = {"fast_build_1_rank": timed("fast", 1, one, 1), "parity_build_all_ranks": timed("parity", ncores, max(3, min(steps, 10)), 1),
+                           "parity_build_1_rank": timed("parity", 1, one, 1)}
+    return res
 
 
 def run_reference(args, rank):
     if rank != 0:
         return 0
     wl = args.workload
-    sample = args.cpu_sample_cells or 4_000_000
-    res = cpu_arm(wl, args.steps, args.warmup, sample)
+    res = cpu_arm(wl, args.steps, args.warmup, args.cpu_sample_cells)
     fset, n, S, bias, avg, diag, desc = WORKLOADS[wl]
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -184,7 +209,7 @@ def run_reference(args, rank):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s: %s" % (wl, desc), "cells_per_grid": n, "formula_set": fset, "surface_types": S,
                    "note": "reference cannot be compiled here (Fortran+MPI+netCDF+OASIS, no Fortran compiler): CPU arm is the oracle port in the reference's loop structure"},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "variants") if k in res},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -195,7 +220,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 200; 1000 for C5, BASELINE.json configs[4])")
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
@@ -219,6 +244,8 @@ def main():
                     help="N>1 diagnostics exchange: peer mailboxes written by the step's kernel over NVLink (default; falls back "
                          "to NCCL when CUDA IPC is unavailable) or ncclAllReduce on a side stream")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1000 if (args.workload == "C5" and args.impl == "b200") else 200
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -239,6 +266,9 @@ def main():
     if m.lib.fc_device_count() < 1:
         raise SystemExit("bench.py: no sm_100 device visible; the flux calculator has no CPU fallback")
     device = local_rank
+    # host buffers of this rank next to its GPU (pinned allocations below are first touched by this thread)
+    all_cpus = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    numa_bound = m.lib.fc_bind_thread_to_device_numa(device) == 0
     fset, n_total, S, bias, avg, diag, desc = WORKLOADS[args.workload]
     if args.cells:
         n_total = args.cells
@@ -290,6 +320,10 @@ def main():
             dist.broadcast_object_list(uid, src=0)
             fc.comm_init(uid[0], rank, world)
 
+    # C5 (BASELINE.json configs[4]): "batched consecutive coupling steps, device resident" = ONE fc_run_steps call for the
+    # whole timed region (CUDA graphs of 32 step launches per calendar month; the bias month advances with timestep = 600 s)
+    batched = args.workload == "C5"
+
     def one_step(k):
         fc.step_all(600 * k)
         if diag and world > 1:
@@ -309,16 +343,36 @@ def main():
     if os.environ.get("FC_BENCH_NO_SAMPLER") != "1":      # tuning aid: rule out the NVML polling as a perturbation
         sampler.start()
     barrier()
+    if batched:
+        fc.set_option("profile_kernel", 0)
+        fc.run_steps(600 * args.warmup, 600, 64)      # graphs captured and instantiated before the clock starts
+        barrier()
+        launches0 = fc.info("launches")
     fc.event_record(0)
-    for k in range(args.steps):
-        one_step(args.warmup + k)
+    if batched:
+        fc.run_steps(600 * (args.warmup + 64), 600, args.steps)
+        if diag and world > 1:
+            fc.allreduce_diagnostics()
+    else:
+        for k in range(args.steps):
+            one_step(args.warmup + k)
     fc.event_record(1)
     ms_total = fc.event_elapsed_ms()
     barrier()
     clocks = sampler.stop()
+    graph_launches = fc.info("graph_launches")
+    launches = fc.info("launches") - launches0
+    last_t = 600 * (args.warmup + args.steps - 1)
+    if batched:      # kernel time for the roofline: a short loop of single steps with event pairs, outside the timed region
+        fc.set_option("profile_kernel", args.profile_stride)
+        for k in range(64):
+            last_t = 600 * (args.warmup + 64 + args.steps + k)
+            fc.step_all(last_t)
+        if diag and world > 1:
+            fc.allreduce_diagnostics()
+        fc.synchronize()
     kern_ms, kern_cnt = fc.kernel_time_ms()
     fc.set_option("profile_kernel", 0)
-    launches = fc.info("launches") - launches0
     exact_calls = fc.info("exact_path_calls")
     if os.environ.get("FC_BENCH_PER_RANK") == "1":
         sys.stderr.write("rank %d: %.4f ms/step, bracketed kernel %.4f ms, cells %d\n" % (rank, ms_total / args.steps, kern_ms / max(kern_cnt, 1), size))
@@ -340,7 +394,11 @@ def main():
     # the slowest rank's kernel processes `size` cells of each grid per launch
     max_size = max(m.shard_range(n_total, r, world, 512)[1] for r in range(world))
     achieved = bytes_per_cell * max_size / (kern_avg_ms * 1e-3) / 1e9
+    achieved_step = bytes_per_cell * max_size / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "achieved_from_ms_per_step": achieved_step, "frac_from_ms_per_step": achieved_step / peak,
+                "note": "frac: launches bracketed by event pairs (an event between two launches switches their programmatic "
+                        "overlap off); frac_from_ms_per_step: the same bytes over the timed region's time per step",
                 "traffic": None, "kernel": "flux_spec_kernel" if fc.info("spec_kernel") == 1 else "fused_step_kernel",
                 "kernel_ms": kern_avg_ms,
                 "algorithmic_bytes_per_cell": bytes_per_cell, "cells_per_launch": max_size, "peak_source": peak_src}
@@ -363,7 +421,7 @@ def main():
         o_in, o_out = small.clone()
         orc = Oracle(small.n, small.S)
         small.apply(orc, o_in, o_out)
-        orc.step_all(600 * (args.warmup + args.steps - 1))
+        orc.step_all(last_t)
         small.inputs = o_in
         got = {k: wrapped[id(g_out[k])].download()[:ns] for k in o_out}
         worst = max(check_scenario(small, got, o_out).values())
@@ -371,10 +429,32 @@ def main():
                   "tolerance": "bit-exact without a transcendental upstream, else %g ulp of (|ref| + cancelling terms) per cell (tests/tolerances.py)" % K_ULP}
 
     diag_sample = None
+    diag_check = None
     if diag:
         s_, mn_, mx_ = fc.diagnostics(1, 1, "HSEN")
         nn = lambda v: None if v != v else v      # NaN (min/max are only computed at diagnostics level 2) -> null
         diag_sample = {"HSEN_type1": {"sum_area_x": s_, "min": nn(mn_), "max": nn(mx_)}}
+        # the (global) diagnostics of the last step against numpy over the outputs of ALL ranks
+        local = {}
+        for k in sorted(g_out):
+            x = wrapped[id(g_out[k])].download()
+            a = sc.area[k[1]]
+            local[k] = (float(np.sum(a * x)), float(np.sum(np.abs(a * x))))
+        parts = [local]
+        if dist:
+            parts = [None] * world
+            dist.all_gather_object(parts, local)
+        worst = 0.0
+        for k in sorted(local):
+            ref = sum(p_[k][0] for p_ in parts)
+            mag = sum(p_[k][1] for p_ in parts)
+            got = fc.diagnostics(*k)[0]
+            dev = abs(got - ref) / mag if mag > 0 else abs(got - ref)
+            worst = max(worst, dev)
+            if dev > 1e-11:
+                raise SystemExit("bench.py: rank %d: global diagnostics of %s differ from numpy over all ranks: %r vs %r" % (rank, k, got, ref))
+        diag_check = {"fields": len(local), "ranks": world, "worst_deviation_over_sum_abs": worst, "bound": 1e-11,
+                      "what": "sum_j area_j * x_j of every output of the last step: the library's (all-reduced) value against numpy over the outputs gathered from all ranks"}
 
     # ---------------- end-to-end through the C ABI with host arrays ----------------
     e2e = None
@@ -400,6 +480,13 @@ def main():
             for g in (1, 2, 3):
                 fh.set_area(g, sc.area[g])
             fh.set_option("diagnostics", 1)
+        # what the reference's own configuration would move: the ice fraction of a surface type is a namelist constant
+        # (val_bottom_var_*, flux_calculator.F90:444-449: written once, never received), and only the send list goes back
+        # to the coupler (oasis_put) -- QSUR is an intermediate
+        for (i, g, name) in h_in:
+            if name == "FICE" and i >= 1:
+                fh.mark_static(i, g, "FICE")
+        fh.set_option("download", 1)
         fh.prepare()
         fh.step_all(0)
         fh.synchronize()
@@ -422,13 +509,16 @@ def main():
             h2d, d2h = int(b[0]), int(b[1])
         e2e = {"value": n_total * args.e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt / args.e2e_steps * 1e3, "steps": args.e2e_steps,
-               "how": "fc_step_all on pinned host arrays: chunked H2D -> fused kernel -> D2H over 3 streams, wall clock with sync on both sides, max over ranks",
+               "how": "fc_step_all on pinned host arrays: chunked H2D -> fused kernel -> D2H over 3 streams, wall clock with sync on both sides, max over ranks; "
+                      "every received field travels every step (FICE is a namelist constant: once), the send list comes back",
                "check": chk}
         fh.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_arm(args.workload, 3, 1, args.cpu_sample_cells or 4_000_000)
+        if all_cpus:
+            os.sched_setaffinity(0, all_cpus)      # the CPU arm gets every core the job has, not just the GPU's socket
+        cpu = cpu_arm(args.workload, 10, 2, args.cpu_sample_cells, variants=False)
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
@@ -443,7 +533,8 @@ def main():
                                                 "nccl": "ncclAllReduce on a side stream"}[comm_used],
                        "l2": "inputs exceed L2 (%.0f MB per step per GPU vs 126 MB), no flush" % (bytes_per_cell * max_size / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "parity": parity, "diagnostics_sample": diag_sample, "exact_path_calls": exact_calls,
+            "parity": parity, "diagnostics_sample": diag_sample, "diagnostics_check": diag_check, "exact_path_calls": exact_calls,
+            "graph_launches": graph_launches, "host_numa_bound": numa_bound,
         }
         print(json.dumps(line))
     if dist:

@@ -10,5 +10,5 @@ from ._lib import lib, LIB_PATH, FluxCalcError, SIGNATURES        # noqa: F401
 from .fields import IDX, VARNAMES, METHODS                         # noqa: F401
 from .memory import DeviceArray, pinned_empty, pinned_free         # noqa: F401
 from . import flux_library                                         # noqa: F401
-from .flux_calculator_calculate import (FluxCalculator, comm_get_unique_id, current_month,  # noqa: F401
-                                        namelist_get, nc_read_var, shard_range)
+from .flux_calculator_calculate import (FluxCalculator, NamelistCalculator, comm_get_unique_id, current_month,  # noqa: F401
+                                        namelist_get, namelist_registry, nc_read_var, shard_range)

@@ -58,6 +58,19 @@ SIGNATURES = {
     # level 2
     "fc_create": (C.c_int, [C.POINTER(ctx_p), c_int64_p, C.c_int, C.c_int]),
     "fc_destroy": (C.c_int, [ctx_p]),
+    "fc_set_allocated": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fc_create_from_namelist": (C.c_int, [C.POINTER(ctx_p), C.c_char_p, C.c_int, c_int64_p, C.c_int]),
+    "fc_num_input_fields": (C.c_int, [ctx_p]),
+    "fc_num_output_fields": (C.c_int, [ctx_p]),
+    "fc_input_field": (C.c_int, [ctx_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                 C.POINTER(C.c_void_p), c_int64_p]),
+    "fc_output_field": (C.c_int, [ctx_p, C.c_int, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_void_p), c_int64_p]),
+    "fc_field_pointer": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), c_int64_p]),
+    "fc_namelist_registry": (C.c_int, [C.c_char_p, C.c_int, c_int64_p, C.c_char_p, i64]),
+    "fc_mark_static": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "fc_mark_dirty": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int]),
+    "fc_bind_thread_to_device_numa": (C.c_int, [C.c_int]),
     "fc_bind_field": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, dp, i64]),
     "fc_set_method": (C.c_int, [ctx_p, C.c_char_p, C.c_int, C.c_char_p]),
     "fc_set_distribute_shortwave": (C.c_int, [ctx_p, C.c_int]),

@@ -7,7 +7,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cctype>
 #include <mutex>
+#include <sched.h>
 #include <set>
 #include <unordered_map>
 
@@ -99,6 +101,7 @@ static bool slot_owns(const fc_context *c, int i, int g, int idx)
 {
     const int b = c->slot[i][g][idx];
     if (b < 0) return false;
+    if (c->alloc_flag[i][g][idx] >= 0) return c->alloc_flag[i][g][idx] != 0;      // the host said so (fc_set_allocated)
     for (int ii = 1; ii <= FC_MAX_SURFACE_TYPES; ++ii)
         for (int gg = 1; gg <= 3; ++gg)
             for (int v = 1; v <= FC_MAX_VARNAMES; ++v)
@@ -153,7 +156,11 @@ static int64_t days_from_civil(int64_t y, int m, int d)
 extern "C" int fc_current_month(int init_date, int64_t seconds)
 {
     const int y = init_date / 10000, m = (init_date / 100) % 100, d = init_date % 100;
-    if (m < 1 || m > 12 || d < 1 || d > 31) return 0;
+    // datetime.strptime(init_date, "%Y%m%d") raises on a date that does not exist (year 1..9999, day within the month)
+    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    if (init_date < 10101 || y < 1 || y > 9999 || m < 1 || m > 12 || d < 1) return 0;
+    const bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+    if (d > mdays[m - 1] + ((m == 2 && leap) ? 1 : 0)) return 0;
     const int64_t shift = seconds >= 0 ? seconds / 86400 : -((-seconds + 86399) / 86400);
     const int64_t z = days_from_civil(y, m, d) + shift + 719468;
     const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
@@ -171,6 +178,9 @@ extern "C" int fc_shard_range(int64_t n, int rank, int nranks, int64_t align, in
     if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks || !offset || !size) return fail(nullptr, FC_ERR_ARG, "fc_shard_range: bad argument");
     if (align < 1) align = 1;
     int64_t part = n / nranks;
+    // the APPLE rule never leaves a rank empty when n >= nranks (decomp_def.F90:23-30): if rounding to `align` would, round to
+    // the largest power-of-two fraction of it that does not (down to single cells; such starts take the guarded tile path)
+    while (align > 1 && part - part % align == 0 && part > 0) align /= 2;
     part -= part % align;
     *offset = rank * part;
     *size = rank < nranks - 1 ? part : n - rank * part;
@@ -301,6 +311,9 @@ extern "C" int fc_create(fc_context **out, const int64_t grid_size[3], int num_s
     for (auto &a : c->slot)
         for (auto &b : a)
             for (auto &v : b) v = -1;
+    for (auto &a : c->alloc_flag)
+        for (auto &b : a)
+            for (auto &v : b) v = -1;
     for (auto &q : c->method)
         for (auto &m : q) m = M_NONE;   // namelist defaults 'none' (flux_calculator.F90:99-107)
     c->consts = make_consts();
@@ -337,6 +350,8 @@ extern "C" int fc_destroy(fc_context *c)
     cudaFree(c->diag_partials);
     cudaFree(c->diag_chunk_out);
     cudaFree(c->tile_ctr);
+    for (auto &g : c->step_graph)
+        if (g) cudaGraphExecDestroy(g);
     p2p_destroy(c);
     for (int b = 0; b < 2; ++b) {
         cudaFree(c->diag_buf[b]);
@@ -354,6 +369,10 @@ extern "C" int fc_destroy(fc_context *c)
         cudaEventDestroy(c->pipe_done[k]);
     }
     cudaStreamDestroy(c->stream);
+    if (c->sa) {
+        standalone_free(*c->sa);
+        delete c->sa;
+    }
     delete c;
     return FC_OK;
 }
@@ -378,7 +397,10 @@ extern "C" int fc_bind_field(fc_context *c, int i, int g, int idx, double *p, in
         release_buffer(c, c->slot[i][g][idx]);
         c->slot[i][g][idx] = -1;
     }
-    if (!p) return FC_OK;   // NULLIFY
+    if (!p) {      // NULLIFY
+        c->alloc_flag[i][g][idx] = -1;
+        return FC_OK;
+    }
     if (n != c->n[g])
         return fail(c, FC_ERR_ARG, "fc_bind_field: %s on %s has %lld elements, grid_size is %lld", kVarNames[idx], kGridNames[g],
                     (long long)n, (long long)c->n[g]);
@@ -413,6 +435,81 @@ extern "C" int fc_bind_field(fc_context *c, int i, int g, int idx, double *p, in
         }
     c->bufs.push_back(B);
     c->slot[i][g][idx] = (int)c->bufs.size() - 1;
+    return FC_OK;
+}
+
+extern "C" int fc_set_allocated(fc_context *c, int i, int g, int idx, int allocated)
+{
+    if (!c) return fail(nullptr, FC_ERR_ARG, "fc_set_allocated: NULL context");
+    if (i < 0 || i > FC_MAX_SURFACE_TYPES || g < 1 || g > 3 || idx < 1 || idx > FC_MAX_VARNAMES)
+        return fail(c, FC_ERR_ARG, "fc_set_allocated: index out of range (surface_type %d, grid %d, var %d)", i, g, idx);
+    c->alloc_flag[i][g][idx] = (signed char)(allocated < 0 ? -1 : (allocated ? 1 : 0));
+    c->dirty = true;
+    return FC_OK;
+}
+
+static int mark_slot(fc_context *c, int i, int g, int idx, const char *fn, Buffer **B)
+{
+    if (!c) return fail(nullptr, FC_ERR_ARG, "%s: NULL context", fn);
+    if (i < 0 || i > FC_MAX_SURFACE_TYPES || g < 1 || g > 3 || idx < 1 || idx > FC_MAX_VARNAMES)
+        return fail(c, FC_ERR_ARG, "%s: index out of range (surface_type %d, grid %d, var %d)", fn, i, g, idx);
+    if (c->slot[i][g][idx] < 0) return fail(c, FC_ERR_STATE, "%s: %s of surface_type %d on grid %d is not bound", fn, kVarNames[idx], i, g);
+    *B = &c->bufs[c->slot[i][g][idx]];
+    return FC_OK;
+}
+
+extern "C" int fc_mark_static(fc_context *c, int i, int g, int idx, int is_static)
+{
+    Buffer *B = nullptr;
+    if (int rc = mark_slot(c, i, g, idx, "fc_mark_static", &B)) return rc;
+    B->is_static = is_static != 0;
+    B->dev_valid = false;
+    return FC_OK;
+}
+
+extern "C" int fc_mark_dirty(fc_context *c, int i, int g, int idx)
+{
+    Buffer *B = nullptr;
+    if (int rc = mark_slot(c, i, g, idx, "fc_mark_dirty", &B)) return rc;
+    B->dev_valid = false;
+    return FC_OK;
+}
+
+// CPUs next to the device's PCIe root: pinned buffers allocated (first touched) afterwards land in that NUMA node, and
+// the copies of eight ranks do not all cross the socket interconnect
+extern "C" int fc_bind_thread_to_device_numa(int device)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, FC_ERR_CUDA, "fc_bind_thread_to_device_numa: no PCI bus id for device %d", device);
+    }
+    for (char *q = bus; *q; ++q) *q = (char)tolower(*q);
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return fail(nullptr, FC_ERR_STATE, "fc_bind_thread_to_device_numa: cannot read %s", path);
+    char line[4096] = {0};
+    const bool got = fgets(line, sizeof line, f) != nullptr;
+    fclose(f);
+    if (!got) return fail(nullptr, FC_ERR_STATE, "fc_bind_thread_to_device_numa: %s is empty", path);
+    cpu_set_t set, allowed;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return fail(nullptr, FC_ERR_STATE, "sched_getaffinity failed");
+    int ncpu = 0;
+    for (char *tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int k = sscanf(tok, "%d-%d", &lo, &hi);
+        if (k == 1) hi = lo;
+        if (k < 1) continue;
+        for (int cpu = lo; cpu <= hi && cpu < CPU_SETSIZE; ++cpu)
+            if (CPU_ISSET(cpu, &allowed)) {      // stay inside what the job was given (cgroup / taskset)
+                CPU_SET(cpu, &set);
+                ++ncpu;
+            }
+    }
+    if (ncpu == 0) return fail(nullptr, FC_ERR_STATE, "fc_bind_thread_to_device_numa: none of the device's local CPUs is available to this process");
+    if (sched_setaffinity(0, sizeof set, &set) != 0) return fail(nullptr, FC_ERR_STATE, "sched_setaffinity failed");
     return FC_OK;
 }
 
@@ -463,16 +560,19 @@ extern "C" int fc_set_corrections(fc_context *c, int which, const double *corr, 
         bool is_dev, is_pin;
         classify_pointer(corr, &is_dev, &is_pin, nullptr);
         const double *src = corr;
-        double *tmp = nullptr;
+        struct Tmp {      // freed on every path out of this block
+            double *p = nullptr;
+            ~Tmp() { cudaFree(p); }
+        } tmp;
         if (!is_dev) {
-            CUDA_TRY(c, cudaMalloc(&tmp, (size_t)n * 12 * sizeof(double)));
-            CUDA_TRY(c, cudaMemcpyAsync(tmp, corr, (size_t)n * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-            src = tmp;
+            CUDA_TRY(c, cudaMalloc(&tmp.p, (size_t)n * 12 * sizeof(double)));
+            CUDA_TRY(c, cudaMemcpyAsync(tmp.p, corr, (size_t)n * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            src = tmp.p;
         }
         if (launch_transpose_corrections(src, c->corr_dev, n, c->stream)) return fail(c, FC_ERR_CUDA, "transpose_corrections launch failed");
         c->launches++;
+        c->tail_own_step = false;
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (tmp) cudaFree(tmp);
     }
     c->corr_enabled = true;
     return FC_OK;
@@ -525,6 +625,9 @@ extern "C" int fc_set_option(fc_context *c, const char *name, int64_t value)
     else if (!strcmp(name, "diagnostics")) c->diagnostics = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(name, "staged")) c->use_staged = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(name, "early_loads")) c->early_loads = value != 0;
+    else if (!strcmp(name, "graphs")) c->use_graphs = value != 0;
+    else if (!strcmp(name, "download")) c->download_sent_only = value != 0;
+    else if (!strcmp(name, "dyn_min_tiles")) c->dyn_min_tiles = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
     else if (!strcmp(name, "stream_touched")) {      // the caller enqueued own work on fc_get_stream(): no shortcut across it
         c->tail_own_step = false;
         return FC_OK;
@@ -1204,6 +1307,7 @@ static bool build_fused(fc_context *c, bool do_early, bool do_normal, FusedBundl
         if (P.diag_n == 0) P.diag = 0;
     }
     P.staged = c->use_staged;
+    P.dyn_min_tiles = c->dyn_min_tiles;
     F.in_bufs.assign(ins.begin(), ins.end());
     F.out_bufs.assign(outs.begin(), outs.end());
     F.ok = true;
@@ -1234,6 +1338,11 @@ static int prepare_impl(fc_context *c, int strict)
                 return fail(c, FC_ERR_MISSING, "diagnostics are enabled but fc_set_area was not called for the %s", kGridNames[g]);
     if (c->corr_enabled && !c->corr_dev) return fail(c, FC_ERR_STATE, "corrections enabled without data");
     for (int k = 0; k < 3; ++k) c->fused[k] = FusedBundle();
+    for (auto &g : c->step_graph)
+        if (g) {
+            cudaGraphExecDestroy(g);
+            g = nullptr;
+        }
     if (!c->force_generic) {
         build_fused(c, true, false, c->fused[0]);
         build_fused(c, false, true, c->fused[1]);
@@ -1382,6 +1491,7 @@ static int ensure_diag_storage(fc_context *c, FusedPlan &P, int K)
     }
     P.diag_partials = c->diag_partials;
     P.diag_rows = rows;
+    if (K == 1) c->diag_rows_1 = rows;
     // result buffer of this step; if its previous all-reduce is still in flight on the side stream, wait for it
     const int b = c->diag_cur ^ 1;
     if (c->comm_busy[b]) {
@@ -1456,17 +1566,107 @@ static void diag_step_done(fc_context *c, const FusedPlan &P, const FusedBundle 
 }
 
 // dynamic schedule: give launch Q claim counter `slot`; returns by how much the launch will advance it
-static int attach_tile_counter(fc_context *c, FusedPlan &Q, int slot, unsigned int *claims)
+static int ensure_tile_counters(fc_context *c)
 {
-    *claims = fused_dyn_claims(Q);
-    if (*claims == 0) return FC_OK;
     if (!c->tile_ctr) {
         CUDA_TRY(c, cudaMalloc(&c->tile_ctr, sizeof(unsigned int) * (kMaxChunks + 2)));
         CUDA_TRY(c, cudaMemset(c->tile_ctr, 0, sizeof(unsigned int) * (kMaxChunks + 2)));
         memset(c->tile_base, 0, sizeof c->tile_base);
     }
+    return FC_OK;
+}
+
+static int attach_tile_counter(fc_context *c, FusedPlan &Q, int slot, unsigned int *claims)
+{
+    *claims = fused_dyn_claims(Q);
+    if (*claims == 0) return FC_OK;
+    if (int rc = ensure_tile_counters(c)) return rc;
     Q.tile_counter = c->tile_ctr + slot;
     Q.tile_base = c->tile_base[slot];
+    return FC_OK;
+}
+
+// geometry facts of a bundle's plan that do not change from step to step (cached: each costs a plan build)
+static void bundle_geometry(FusedBundle &F, const FusedPlan &P)
+{
+    if (F.geom_cached) return;
+    F.spec = fused_uses_spec(P) != 0;
+    F.claims = F.spec ? fused_dyn_claims(P) : 0u;
+    F.fills = F.spec && fused_fills_device(P) != 0;
+    F.geom_cached = true;
+}
+
+// one device-resident step on the context's stream.  gstep < 0: an ordinary step.  gstep >= 0: step number gstep of a
+// sequence that is being captured into a CUDA graph (fc_run_steps): nothing here may depend on state that changes
+// between two launches of that graph -- no fold of the previous step's rows (only the last step's diagnostics are
+// ever read; the caller registers them after the graph), one row set, tile counters that the graph's leading memset
+// node zeroes (step s uses counter s mod 2 at base (s / 2) * claims), no event records, no allocation.
+static int launch_resident(fc_context *c, FusedBundle &F, FusedPlan &P, int gstep)
+{
+    const bool graph = gstep >= 0;
+    bundle_geometry(F, P);
+    const bool spec = F.spec;
+    int nlaunch = 0;
+    // rows of the previous specialised step that nobody folded yet: this launch folds them while its ring fills,
+    // unless it is not that kind of launch
+    if (!graph && c->fold_pending && !(spec && P.diag))
+        if (int rc = flush_fold(c)) return rc;
+    if (P.diag) {
+        if (!graph)
+            if (int rc = ensure_diag_storage(c, P, 1)) return rc;
+        const int b = c->diag_cur ^ 1;
+        P.diag_partials = c->diag_partials;
+        P.diag_rows = c->diag_rows_1;
+        P.diag_out = c->diag_buf[b];
+        diag_chunk_view(c, P, graph ? 0 : (c->row_set ^= 1), 1, P);
+        if (!graph && c->fold_pending) P.fold_prev = c->fold;
+    }
+    P.early_loads = (spec && c->early_loads && (graph ? gstep > 0 : c->tail_own_step)) ? 1 : 0;
+    // dynamic schedule: consecutive steps alternate between two counters, because the producers of a step may claim
+    // while the previous step still runs.  That holds for at most two steps at a time only if this step's grid
+    // fills the device (a third step finds no room before the first has left); smaller grids wait first.
+    const unsigned int claims = F.claims;
+    const int tslot = kMaxChunks + (graph ? (gstep & 1) : (c->tile_par ^= 1));
+    if (claims && !graph)
+        if (int rc = ensure_tile_counters(c)) return rc;
+    if (claims) {
+        P.tile_counter = c->tile_ctr + tslot;
+        P.tile_base = graph ? (unsigned int)(gstep >> 1) * claims : c->tile_base[tslot];
+    }
+    if (claims && !F.fills) P.early_loads = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!graph && c->profile_kernel && c->prof_used < 8192 && (c->prof_seq++ % c->profile_kernel) == 0) {
+        while (c->prof_ev.size() < c->prof_used + 2) {
+            cudaEvent_t e;
+            CUDA_TRY(c, cudaEventCreate(&e));
+            c->prof_ev.push_back(e);
+        }
+        e0 = c->prof_ev[c->prof_used];
+        e1 = c->prof_ev[c->prof_used + 1];
+        c->prof_used += 2;
+        CUDA_TRY(c, cudaEventRecord(e0, c->stream));
+    }
+    if (launch_fused(P, c->stream, &nlaunch)) return fail(c, FC_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (e1) CUDA_TRY(c, cudaEventRecord(e1, c->stream));
+    c->launches += nlaunch;
+    if (!graph) {
+        c->tile_base[tslot] += claims;
+        c->fold_pending = false;      // (the launch took the previous step's rows along)
+        c->tail_own_step = spec;
+    }
+    if (P.diag) {
+        if (spec) {
+            if (!graph) {
+                c->fold = make_fold(P);
+                c->fold_pending = true;
+            }
+        } else if (int rc = finalize_chunk(c, P, c->stream)) {
+            return rc;
+        }
+        if (!graph) diag_step_done(c, P, F);
+    }
+    if (!F.extra.empty())
+        if (int rc = run_ops(c, F.extra)) return rc;
     return FC_OK;
 }
 
@@ -1485,63 +1685,32 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     if (async_device_only && any_host) return fail(c, FC_ERR_STATE, "fc_run_steps needs device-resident fields (bind device pointers)");
     int nlaunch = 0;
 
-    if (!any_host) {
-        const bool spec = fused_uses_spec(P) != 0;
-        // rows of the previous specialised step that nobody folded yet: this launch folds them while its ring fills,
-        // unless it is not that kind of launch
-        if (c->fold_pending && !(spec && P.diag))
-            if (int rc = flush_fold(c)) return rc;
-        if (P.diag) {
-            if (int rc = ensure_diag_storage(c, P, 1)) return rc;
-            diag_chunk_view(c, P, c->row_set ^= 1, 1, P);
-            if (c->fold_pending) P.fold_prev = c->fold;
-        }
-        P.early_loads = (spec && c->tail_own_step && c->early_loads) ? 1 : 0;
-        // dynamic schedule: consecutive steps alternate between two counters, because the producers of a step may claim
-        // while the previous step still runs.  That holds for at most two steps at a time only if this step's grid
-        // fills the device (a third step finds no room before the first has left); smaller grids wait first.
-        unsigned int claims = 0;
-        const int tslot = kMaxChunks + (c->tile_par ^= 1);
-        if (spec)
-            if (int rc = attach_tile_counter(c, P, tslot, &claims)) return rc;
-        if (claims && !fused_fills_device(P)) P.early_loads = 0;
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (c->profile_kernel && c->prof_used < 8192 && (c->prof_seq++ % c->profile_kernel) == 0) {
-            while (c->prof_ev.size() < c->prof_used + 2) {
-                cudaEvent_t e;
-                CUDA_TRY(c, cudaEventCreate(&e));
-                c->prof_ev.push_back(e);
-            }
-            e0 = c->prof_ev[c->prof_used];
-            e1 = c->prof_ev[c->prof_used + 1];
-            c->prof_used += 2;
-            CUDA_TRY(c, cudaEventRecord(e0, c->stream));
-        }
-        if (launch_fused(P, c->stream, &nlaunch)) return fail(c, FC_ERR_CUDA, "fused launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (e1) CUDA_TRY(c, cudaEventRecord(e1, c->stream));
-        c->launches += nlaunch;
-        c->tile_base[tslot] += claims;
-        c->fold_pending = false;      // (the launch took the previous step's rows along)
-        c->tail_own_step = spec;
-        if (P.diag) {
-            if (spec) {
-                c->fold = make_fold(P);
-                c->fold_pending = true;
-            } else if (int rc = finalize_chunk(c, P, c->stream)) {
-                return rc;
-            }
-            diag_step_done(c, P, F);
-        }
-        if (!F.extra.empty())
-            if (int rc = run_ops(c, F.extra)) return rc;
-        return FC_OK;
-    }
+    if (!any_host) return launch_resident(c, F, P, -1);
 
     // host-pointer mode: chunked H2D -> kernel -> D2H pipeline over three streams (copy engines
     // and SMs overlap; inputs of chunk k+1 travel while chunk k computes and chunk k-1 returns)
     int64_t nmax = std::max(c->n[1], std::max(c->n[2], c->n[3]));
+    // pipeline depth: the first chunk's upload and the last chunk's download are exposed, so even a small shard (the 8-GPU
+    // share of a 10^7-cell grid is 1.25 * 10^6 cells) gets at least 8 chunks; tiny grids are not worth splitting
     const int K = c->h2d_chunks > 0 ? std::min(c->h2d_chunks, kMaxChunks)
-                                    : (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(1, nmax / 262144));
+                  : (nmax < 65536 ? 1 : (int)std::min<int64_t>(kMaxChunks, std::max<int64_t>(8, nmax / 262144)));
+    // what travels: inputs the host may have rewritten (everything not marked static, and static arrays not uploaded
+    // yet), results the host will read (everything computed, or with option "download" = 1 only the registered output
+    // fields -- what the reference hands to oasis_put, flux_calculator.F90:909-936,999-1026)
+    std::vector<int> up, down;
+    for (int b : F.in_bufs) {
+        const Buffer &B = c->bufs[b];
+        if (!B.user_is_device && !(B.is_static && B.dev_valid)) up.push_back(b);
+    }
+    {
+        std::set<int> sent;
+        const bool sent_only = c->download_sent_only && F.extra.empty();
+        if (sent_only)
+            for (const OutputField &o : c->outputs)
+                if (c->slot[o.surface_type][o.grid][o.idx] >= 0) sent.insert(c->slot[o.surface_type][o.grid][o.idx]);
+        for (int b : F.out_bufs)
+            if (!c->bufs[b].user_is_device && (!sent_only || sent.count(b))) down.push_back(b);
+    }
     if (int rc = flush_fold(c)) return rc;
     if (P.diag)
         if (int rc = ensure_diag_storage(c, P, K)) return rc;
@@ -1551,9 +1720,8 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
         cudaStream_t s = c->pipe[k % 3];
         int64_t c0[4], c1[4];
         chunk_range(c, k, K, c0, c1);
-        for (int b : F.in_bufs) {
+        for (int b : up) {
             const Buffer &B = c->bufs[b];
-            if (B.user_is_device) continue;
             const int64_t cnt = c1[B.grid] - c0[B.grid];
             if (cnt <= 0) continue;
             CUDA_TRY(c, cudaMemcpyAsync(B.dev + c0[B.grid], B.user + c0[B.grid], (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -1573,9 +1741,8 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
                 return rc;
             }
         }
-        for (int b : F.out_bufs) {
+        for (int b : down) {
             const Buffer &B = c->bufs[b];
-            if (B.user_is_device) continue;
             const int64_t cnt = c1[B.grid] - c0[B.grid];
             if (cnt <= 0) continue;
             CUDA_TRY(c, cudaMemcpyAsync(B.user + c0[B.grid], B.dev + c0[B.grid], (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1584,6 +1751,7 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     }
     c->launches += nlaunch;
     for (int k = 0; k < 3; ++k) CUDA_TRY(c, cudaStreamSynchronize(c->pipe[k]));
+    for (int b : up) c->bufs[b].dev_valid = true;
     if (P.diag) {
         if (K > 1) {      // fold the chunks' result vectors in chunk order
             if (launch_diag_combine(c->diag_chunk_out, K, P.diag_out, c->stream)) return fail(c, FC_ERR_CUDA, "diag combine launch failed");
@@ -1596,12 +1764,72 @@ static int run_fused(fc_context *c, FusedBundle &F, bool async_device_only)
     return FC_OK;
 }
 
+// do_regridding (flux_calculator_basic.F90:463-522) of variable idx for surface type st (0 = all), in the reference's
+// order u->t, v->t, t->u, t->v, for a context that knows the namelist's regridding requests (fc_create_from_namelist)
+static int sa_regrid_var(fc_context *c, int idx, int st)
+{
+    static const int from[4] = {2, 3, 1, 1}, to[4] = {1, 1, 2, 3};
+    Standalone &R = *c->sa;
+    for (int j = 1; j <= FC_MAX_SURFACE_TYPES; ++j) {
+        if (!(j == st || st == 0)) continue;
+        for (int d = 0; d < 4; ++d) {
+            const SaSlot &src = R.slot[j][from[d]][idx], &dst = R.slot[j][to[d]][idx];
+            if (!src.put[to[d]] || src.arr < 0 || dst.arr < 0) continue;
+            if (!c->regrid[d].set)
+                return fail(c, FC_ERR_STATE, "the namelist asks for regridding %s from the %s to the %s but no matrix was set (fc_set_regrid_matrix, direction %d)",
+                            kVarNames[idx], kGridNames[from[d]], kGridNames[to[d]], d);
+            if (int rc = fc_regrid(c, d, R.arrays[(size_t)dst.arr].host, R.arrays[(size_t)src.arr].host)) return rc;
+        }
+    }
+    return FC_OK;
+}
+
+// received fields of one phase (flux_calculator.F90:891-896 early, :961-966 normal)
+static int sa_regrid_inputs(fc_context *c, bool early)
+{
+    for (const SaField &f : c->sa->in)
+        if (f.early == early)
+            if (int rc = sa_regrid_var(c, f.idx, f.type)) return rc;
+    return FC_OK;
+}
+
 static int step_impl(fc_context *c, int which, int64_t t, bool async_device_only)
 {
     if (int rc = ensure_prepared(c)) return rc;
     cudaSetDevice(c->device);
     c->time = t;                       // current_step_time (flux_calculator.F90:861)
     c->h2d_bytes = c->d2h_bytes = 0;
+    if (c->sa && !c->sa->regrid.empty()) {
+        if (which == 0 || which == 2)
+            if (int rc = sa_regrid_inputs(c, true)) return rc;
+        if (which == 1 || which == 2)
+            if (int rc = sa_regrid_inputs(c, false)) return rc;
+        if (c->sa->regrid.size() > c->sa->n_input_regrid) {
+            // a COMPUTED field is regridded between two calculators (flux_calculator.F90:903, :975-989): the reference's pass
+            // sequence, one calculator at a time
+            if (c->diagnostics) return fail(c, FC_ERR_STATE, "diagnostics need the fused path, but regridding of computed fields requires the pass sequence");
+            auto pass = [&](int (*gen)(Gen &), int idx) -> int {
+                Gen G{c, {}, "", false};
+                if (int rc = gen(G)) return rc;
+                if (int rc = run_ops(c, G.ops)) return rc;
+                return idx ? sa_regrid_var(c, idx, 0) : FC_OK;
+            };
+            if (which == 0 || which == 2) {
+                if (int rc = pass([](Gen &G) { return gen_rbbr(G); }, FC_RBBR)) return rc;
+                if (int rc = pass([](Gen &G) { return gen_send(G, true); }, 0)) return rc;
+            }
+            if (which == 1 || which == 2) {
+                if (int rc = pass([](Gen &G) { int r = gen_qsur(G, 1); if (!r) r = gen_qsur(G, 2); if (!r) r = gen_qsur(G, 3); return r; }, FC_QSUR)) return rc;
+                if (int rc = pass([](Gen &G) { return gen_meva(G); }, FC_MEVA)) return rc;
+                if (int rc = pass([](Gen &G) { return gen_hlat(G); }, FC_HLAT)) return rc;
+                if (int rc = pass([](Gen &G) { return gen_hsen(G); }, FC_HSEN)) return rc;
+                if (int rc = pass([](Gen &G) { return gen_mom(G, 2, 0); }, FC_UMOM)) return rc;
+                if (int rc = pass([](Gen &G) { return gen_mom(G, 3, 1); }, FC_VMOM)) return rc;
+                if (int rc = pass([](Gen &G) { int r = gen_rsdr(G, false); if (!r) r = gen_send(G, false); return r; }, 0)) return rc;
+            }
+            return FC_OK;
+        }
+    }
     FusedBundle &F = c->fused[which];
     if (F.ok) return run_fused(c, F, async_device_only);
     if (async_device_only) {
@@ -1621,11 +1849,101 @@ extern "C" int fc_step_early(fc_context *c, int64_t t) { return step_impl(c, 0, 
 extern "C" int fc_step_normal(fc_context *c, int64_t t) { return step_impl(c, 1, t, false); }
 extern "C" int fc_step_all(fc_context *c, int64_t t) { return step_impl(c, 2, t, false); }
 
+// ---------------------------------------------------------------------------------------------
+// fc_run_steps: consecutive coupling steps as CUDA graphs (the time loop of flux_calculator.F90:859-1028 with the
+// fields resident on the device).  The only thing that changes from step to step is the month slab of the bias
+// corrections (calculate.F90:66-73,112-116), so the steps of one calendar month are replays of ONE captured graph of
+// kGraphSteps step launches (programmatic dependent launch edges between them are captured as such); what is left
+// over at the end of a month is issued directly.  Graphs are kept per (month, length) until the next fc_prepare.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int kGraphSteps = 32;      // step launches per graph (even: the tile counters alternate)
+
+int capture_steps(fc_context *c, FusedBundle &F, int month, int nsteps, cudaGraphExec_t *exec)
+{
+    FusedPlan P0 = F.plan;
+    if (P0.t.bias) P0.t.bias = c->corr_dev + (size_t)(month - 1) * (size_t)c->n[1];
+    // everything that allocates or synchronises happens before the capture
+    if (int rc = flush_fold(c)) return rc;
+    bundle_geometry(F, P0);
+    if (F.claims)
+        if (int rc = ensure_tile_counters(c)) return rc;
+    if (P0.diag)
+        if (int rc = ensure_diag_storage(c, P0, 1)) return rc;
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = FC_OK;
+    if (F.claims && cudaMemsetAsync(c->tile_ctr + kMaxChunks, 0, 2 * sizeof(unsigned int), c->stream) != cudaSuccess)
+        rc = fail(c, FC_ERR_CUDA, "fc_run_steps: memset node failed");
+    for (int s = 0; s < nsteps && rc == FC_OK; ++s) {
+        FusedPlan P = P0;
+        rc = launch_resident(c, F, P, s);
+    }
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != FC_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess || !graph) return fail(c, FC_ERR_CUDA, "fc_run_steps: stream capture failed: %s", cudaGetErrorString(e));
+    const cudaError_t ei = cudaGraphInstantiate(exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) return fail(c, FC_ERR_CUDA, "fc_run_steps: cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+    return FC_OK;
+}
+}  // namespace
+
 extern "C" int fc_run_steps(fc_context *c, int64_t t0, int64_t dt, int nsteps)
 {
     if (!c || nsteps < 0) return fail(c, FC_ERR_ARG, "fc_run_steps: bad argument");
-    for (int k = 0; k < nsteps; ++k)
-        if (int rc = step_impl(c, 2, t0 + (int64_t)k * dt, true)) return rc;
+    if (int rc = ensure_prepared(c)) return rc;
+    cudaSetDevice(c->device);
+    FusedBundle &F = c->fused[2];
+    bool resident = F.ok;
+    if (resident) {
+        for (int b : F.in_bufs) resident = resident && c->bufs[b].user_is_device;
+        for (int b : F.out_bufs) resident = resident && c->bufs[b].user_is_device;
+        for (const HOp &h : F.extra)
+            for (int b : {h.out, h.in[0], h.in[1]})
+                if (b >= 0) resident = resident && c->bufs[b].user_is_device;
+    }
+    const bool use_graphs = resident && c->use_graphs && !c->profile_kernel;
+    int k = 0;
+    while (k < nsteps) {
+        const int64_t t = t0 + (int64_t)k * dt;
+        const int month = F.ok && F.plan.t.bias ? fc_current_month(c->init_date, t) : 1;
+        int run = 1;      // steps k .. k + run - 1 share the month
+        while (k + run < nsteps && (!(F.ok && F.plan.t.bias) || fc_current_month(c->init_date, t0 + (int64_t)(k + run) * dt) == month)) ++run;
+        while (use_graphs && run >= kGraphSteps) {
+            cudaGraphExec_t &g = c->step_graph[month];
+            if (!g)
+                if (int rc = capture_steps(c, F, month, kGraphSteps, &g)) return rc;
+            if (int rc = flush_fold(c)) return rc;      // (a directly issued step before this graph left its rows)
+            CUDA_TRY(c, cudaGraphLaunch(g, c->stream));
+            c->graph_launches += 1;
+            c->launches += (int64_t)kGraphSteps * (1 + (F.extra.empty() ? 0 : 1));
+            k += kGraphSteps;
+            run -= kGraphSteps;
+            // state as the graph leaves it: time, tile counters, the last step's diagnostics rows (set 0) not folded yet
+            c->time = t0 + (int64_t)(k - 1) * dt;
+            if (F.claims) c->tile_base[kMaxChunks] = c->tile_base[kMaxChunks + 1] = (unsigned int)(kGraphSteps / 2) * F.claims;
+            c->tail_own_step = F.spec && F.extra.empty();
+            if (F.plan.diag) {
+                FusedPlan P = F.plan;
+                P.diag_partials = c->diag_partials;
+                P.diag_rows = c->diag_rows_1;
+                P.diag_out = c->diag_buf[c->diag_cur ^ 1];
+                diag_chunk_view(c, P, 0, 1, P);
+                c->row_set = 0;
+                if (F.spec) {
+                    c->fold = make_fold(P);
+                    c->fold_pending = true;
+                }
+                diag_step_done(c, P, F);
+            }
+        }
+        for (int r = 0; r < run; ++r, ++k)
+            if (int rc = step_impl(c, 2, t0 + (int64_t)k * dt, true)) return rc;
+    }
     return FC_OK;
 }
 
@@ -1676,6 +1994,7 @@ extern "C" int64_t fc_get_info(const fc_context *c, const char *name)
 {
     if (!c || !name) return -1;
     if (!strcmp(name, "launches")) return c->launches;
+    if (!strcmp(name, "graph_launches")) return c->graph_launches;
     if (!strcmp(name, "exact_path_calls")) {   // threads that recomputed their cells with the IEEE routines (process-wide)
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);

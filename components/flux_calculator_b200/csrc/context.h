@@ -22,6 +22,8 @@ struct Buffer {
     bool user_is_device = false;
     bool user_is_pinned = false;
     bool registered = false;     // we called cudaHostRegister on it
+    bool is_static = false;      // fc_mark_static: the host does not rewrite it between steps (a namelist constant, val_*)
+    bool dev_valid = false;      // ... and the device mirror already holds it
     int refs = 0;
 };
 
@@ -55,12 +57,49 @@ enum Quantity { Q_QSUR_T = 0, Q_QSUR_U, Q_QSUR_V, Q_MEVA, Q_HLAT, Q_HSEN, Q_MOM,
 
 struct FusedBundle {
     bool ok = false;
+    bool geom_cached = false, spec = false, fills = false;   // step-invariant facts of the plan's geometry (context.cu: bundle_geometry)
+    unsigned int claims = 0;
     FusedPlan plan;
     std::vector<int> in_bufs, out_bufs;   // buffers to upload / download in host-pointer mode
     std::vector<HOp> extra;               // averaging of pass-through variables (run after the fused launch)
     // diagnostics slot -> (surface type, grid, var) of the active slots, compact order
     std::vector<int> diag_slots;
 };
+
+// what fc_create_from_namelist builds from flux_calculator.nml (frontend.cu): the arrays a Fortran host would ALLOCATE and the
+// reference's registry / field lists on top of them
+struct SaArray {
+    int grid = 1;
+    double *host = nullptr;      // page-locked, owned by the context
+    double fill = 0.0;           // constant from the namelist (val_*), or default value of a flux nobody computes (val_flux_*)
+    bool has_fill = false, constant = false;
+};
+struct SaSlot {
+    int arr = -1;                // index into arrays (-1: disassociated); aliases share it
+    bool allocated = false;      // %allocated (basic.F90:88)
+    bool put[4] = {false, false, false, false};      // put_to_t/u/v_grid (basic.F90:89-91), index = destination grid
+};
+struct SaField {
+    std::string name;            // OASIS name: R|S + model letter + variable + two-digit surface type (basic.F90:149, :266)
+    int grid = 1, type = 0, idx = 0;
+    bool early = false;
+};
+struct SaRegrid {
+    int type, idx, from, to;
+};
+struct Standalone {
+    int S = 0;
+    char letter = 'M';
+    int64_t n[4] = {0, 0, 0, 0};
+    std::vector<SaArray> arrays;
+    SaSlot slot[FC_MAX_SURFACE_TYPES + 1][4][FC_MAX_VARNAMES + 1];
+    std::vector<SaField> in, out;
+    std::vector<SaRegrid> regrid;        // in the order prepare_regridding creates them: first those of received fields ...
+    size_t n_input_regrid = 0;           // ... then those of computed ones
+    std::string method[8][FC_MAX_SURFACE_TYPES + 1];
+    std::string warnings;
+};
+void standalone_free(Standalone &R);
 
 extern thread_local std::string g_last_error;
 int fail(fc_context *ctx, int code, const char *fmt, ...);
@@ -90,6 +129,7 @@ struct fc_context {
 
     std::vector<fc::Buffer> bufs;
     int slot[FC_MAX_SURFACE_TYPES + 1][4][FC_MAX_VARNAMES + 1];
+    signed char alloc_flag[FC_MAX_SURFACE_TYPES + 1][4][FC_MAX_VARNAMES + 1];   // %allocated as stated by the host: -1 = infer from aliasing
     int method[fc::Q_COUNT][FC_MAX_SURFACE_TYPES + 1];
     int dist_sw = -1;            // -1 auto, 0 off, 1 on
 
@@ -134,6 +174,7 @@ struct fc_context {
     int tile_par = 0;
     double *diag_chunk_out = nullptr;       // [kMaxChunks][sum|min|max][kDiagSlots]: per-chunk results (host-pointer pipeline)
     size_t diag_chunk_stride = 0;           // doubles of partial rows + reduce scratch per chunk
+    int64_t diag_rows_1 = 0;                // row stride of the device-resident (one launch per step) layout
     double *diag_buf[2] = {nullptr, nullptr};   // [sum|min|max][kDiagSlots] compact slots, double buffered by step
     int diag_cur = 0;                    // buffer the last step wrote
     cudaStream_t comm_stream = nullptr;  // NCCL all-reduce runs here, overlapped with the next step
@@ -163,11 +204,18 @@ struct fc_context {
     size_t prof_used = 0;
     cudaEvent_t user_ev[2] = {nullptr, nullptr};
 
+    fc::Standalone *sa = nullptr;        // set by fc_create_from_namelist
     // front end (frontend.cu): &correctionsctl of the last namelist read, warnings of the corrections loader
     bool nml_read = false;
     bool nml_lcorrections = false;
     std::string warning;
 
+    // fc_run_steps: one instantiated graph of kGraphSteps step launches per calendar month (index 1..12)
+    cudaGraphExec_t step_graph[13] = {};
+    bool use_graphs = true;
+    bool download_sent_only = false;        // option "download" = 1: only registered output fields travel back to the host
+    int dyn_min_tiles = 0;                  // option: tiles per CTA from which the specialised kernel schedules dynamically (0: default)
+    int64_t graph_launches = 0;
     int64_t launches = 0;
     int64_t h2d_bytes = 0, d2h_bytes = 0;   // of the last step call
     std::string err;

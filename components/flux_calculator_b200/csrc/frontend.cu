@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <array>
 #include <fstream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -702,3 +703,604 @@ extern "C" int fc_load_corrections(fc_context *c, const char *root_dir, int64_t 
 }
 
 extern "C" const char *fc_last_warning(const fc_context *c) { return c ? c->warning.c_str() : ""; }
+
+// ---------------------------------------------------------------------------------------------
+// "next" row 4, the rest: the whole /input/ namelist drives a context.
+//
+// fc_create_from_namelist re-does, on top of the C ABI, what the reference's main program does between reading the
+// namelist and the time loop (flux_calculator.F90 STEP 1.4 - 1.7, lines 340-768) with the helpers of
+// flux_calculator_basic.F90 (allocate_localvar :287-308, init_localvar :312-330, distribute_input_field :334-358,
+// add_input_field :128-166, add_output_field :170-283, prepare_regridding :362-459) and flux_calculator_prepare.F90
+// (required-input lists INCLUDING their quirks, 'copy' = pointer alias, everything else allocates the result):
+// the library then owns the host arrays a Fortran host would ALLOCATE, knows which slots alias which, which are
+// %allocated, which fields arrive from the coupler (name, grid, early flag) and which are sent, and what is regridded
+// between the grids when.  tests/golden/step_golden.json holds what the reference's own source text builds for eight
+// namelists (executed by tests/golden/fortran_interp.py); tests/test_standalone.py compares registry and field lists.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxVarsNml = 100;      // MAX_VARS, basic.F90:30
+
+const char *kNames35[FC_MAX_VARNAMES + 1] = {
+    "",     "ALBE", "ALBA", "AMOI", "AMOM", "FARE", "FICE", "PATM", "PSUR", "QATM", "TATM", "TSUR",
+    "UATM", "VATM", "U10M", "V10M", "CMOM", "CMOI", "CHEA", "QSUR", "HLAT", "HSEN", "MEVA", "MPRE",
+    "MRAI", "MSNO", "RBBR", "RLWD", "RLWU", "RSID", "RSIU", "RSIN", "RSDD", "RSDR", "UMOM", "VMOM"};
+
+std::string rtrim(std::string s)
+{
+    while (!s.empty() && s.back() == ' ') s.pop_back();
+    return s;
+}
+
+struct SaBuilder {
+    fc::Standalone &R;
+    const std::vector<NmlGroup> &groups;
+    int m;      // my_bottom_model
+    std::string err;
+    int err_code = FC_OK;
+
+    // namelist arrays with their declared defaults (flux_calculator.F90:62-107)
+    std::vector<NmlValue> get(const char *name, std::vector<int64_t> shape)
+    {
+        std::vector<NmlValue> v;
+        std::string e;
+        if (!nml_resolve(groups, "input", name, shape, v, e) && err.empty()) {
+            err = e;
+            err_code = FC_ERR_ARG;
+        }
+        return v;
+    }
+    static std::string str(const NmlValue &v, const char *dflt) { return v.null ? std::string(dflt) : rtrim(v.text); }
+    static double num(const NmlValue &v, double dflt)
+    {
+        if (v.null) return dflt;
+        std::string t = v.text;
+        for (char &ch : t)
+            if (ch == 'd' || ch == 'D') ch = 'e';
+        return strtod(t.c_str(), nullptr);
+    }
+    static bool flag(const NmlValue &v, bool dflt)
+    {
+        bool b = dflt;
+        if (!v.null) nml_logical(v.text, b);
+        return b;
+    }
+
+    int var_index(const std::string &name) const
+    {
+        for (int i = 1; i <= FC_MAX_VARNAMES; ++i)
+            if (name == kNames35[i]) return i;
+        return 0;
+    }
+    bool stop(int code, const std::string &msg)
+    {
+        if (err.empty()) {
+            err = msg;
+            err_code = code;
+        }
+        return false;
+    }
+    fc::SaSlot &slot(int i, int g, int idx) { return R.slot[i][g][idx]; }
+    bool assoc(int i, int g, int idx) { return slot(i, g, idx).arr >= 0; }
+
+    int new_array(int g, double fill, bool has_fill)
+    {
+        fc::SaArray a;
+        a.grid = g;
+        a.fill = fill;
+        a.has_fill = has_fill;
+        R.arrays.push_back(a);
+        return (int)R.arrays.size() - 1;
+    }
+    // allocate_localvar (basic.F90:287-308)
+    bool allocate_localvar(const std::string &name, int i, int g)
+    {
+        const int idx = var_index(name);
+        if (!idx) return stop(FC_ERR_ARG, "Could not allocate local variable " + name + " because flux_calculator does not know this variable.");
+        fc::SaSlot &s = slot(i, g, idx);
+        s.arr = new_array(g, 0.0, false);
+        s.allocated = true;
+        s.put[1] = s.put[2] = s.put[3] = false;
+        return true;
+    }
+    // distribute_input_field (basic.F90:334-358)
+    void distribute(const std::string &name, int g, int from, int to)
+    {
+        const int idx = var_index(name);
+        for (int j = 1; j <= R.S; ++j)
+            if (j == to || (j != from && to == 0)) slot(j, g, idx).arr = slot(from, g, idx).arr;
+    }
+    // add_input_field (basic.F90:128-166)
+    void add_input(const std::string &name, char letter, int i, int g)
+    {
+        fc::SaField f;
+        char buf[16];
+        snprintf(buf, sizeof buf, "R%c%s%02d", letter, name.c_str(), i);
+        f.name = buf;
+        f.grid = g;
+        f.type = i;
+        f.idx = var_index(name);
+        f.early = name == "FARE" || name == "TSUR" || name == "ALBE" || name == "CMOM" || name == "CMOI" || name == "CHEA";   // :153-155
+        R.in.push_back(f);
+    }
+
+    // one grid's share of STEP 1.4 (flux_calculator.F90:436-476 for t, :477-520 u, :521-563 v)
+    bool receive_grid(int g, const char *suffix)
+    {
+        const std::string sfx(suffix);
+        auto nb = get(("name_bottom_var_" + sfx).c_str(), {10, 10, kMaxVarsNml});
+        auto vb = get(("val_bottom_var_" + sfx).c_str(), {10, 10, kMaxVarsNml});
+        auto na = get(("name_atmos_var_" + sfx).c_str(), {kMaxVarsNml});
+        auto va = get(("val_atmos_var_" + sfx).c_str(), {kMaxVarsNml});
+        if (!err.empty()) return false;
+        for (int i = 1; i <= 10; ++i)
+            for (int j = 1; j <= kMaxVarsNml; ++j) {
+                const size_t k = (size_t)((m - 1) + 10 * (i - 1) + 100 * (j - 1));
+                const std::string name = str(nb[k], "none");
+                if (name == "none") continue;
+                if (!allocate_localvar(name, i, g)) return false;
+                const double val = num(vb[k], -1.0e20);
+                if (val > -0.99e20) {      // a constant from the namelist (init_localvar)
+                    fc::SaArray &a = R.arrays[(size_t)slot(i, g, var_index(name)).arr];
+                    a.fill = val;
+                    a.has_fill = a.constant = true;
+                } else if (val < -1.99e20) {      // -2.0e20: use the field of surface type 1
+                    distribute(name, g, 1, 0);
+                } else {
+                    add_input(name, R.letter, i, g);
+                }
+            }
+        for (int j = 1; j <= kMaxVarsNml; ++j) {
+            const std::string name = str(na[(size_t)j - 1], "none");
+            if (name == "none") continue;
+            if (!allocate_localvar(name, 0, g)) return false;
+            const double val = num(va[(size_t)j - 1], -1.0e20);
+            if (val > -0.99e20) {
+                fc::SaArray &a = R.arrays[(size_t)slot(0, g, var_index(name)).arr];
+                a.fill = val;
+                a.has_fill = a.constant = true;
+            } else {
+                add_input(name, 'A', 0, g);
+            }
+            distribute(name, g, 0, 0);      // every surface type sees the atmosphere's array
+        }
+        return true;
+    }
+
+    // prepare_regridding (basic.F90:362-459) for variable idx, surface type st (0 = all)
+    bool prepare_regridding(int idx, int st, const std::vector<NmlValue> rg[4])
+    {
+        static const int from[4] = {2, 3, 1, 1}, to[4] = {1, 1, 2, 3};      // u->t, v->t, t->u, t->v: the reference's order
+        for (int d = 0; d < 4; ++d)
+            for (int j = 1; j <= 10; ++j) {
+                if (!(j == st || st == 0)) continue;
+                for (int k = 1; k <= kMaxVarsNml; ++k) {
+                    const std::string name = str(rg[d][(size_t)((m - 1) + 10 * (j - 1) + 100 * (k - 1))], "none");
+                    if (name != kNames35[idx]) continue;
+                    fc::SaSlot &dst = slot(j, to[d], idx);
+                    if (dst.allocated)
+                        return stop(FC_ERR_STATE, std::string("Could not regrid local variable ") + kNames35[idx] +
+                                    " as requested in the namelist, because it already exists on that grid.");
+                    dst.arr = new_array(to[d], 0.0, false);
+                    dst.allocated = true;
+                    slot(j, from[d], idx).put[to[d]] = true;
+                    fc::SaRegrid r{j, idx, from[d], to[d]};
+                    R.regrid.push_back(r);
+                }
+            }
+        return true;
+    }
+
+    // the prepare_* routines (flux_calculator_prepare.F90): {tested variable, label in the message} per method, quirks kept
+    struct Need { int tested; const char *label; };
+    bool prepare(const char *var, int out_idx, int i, int g, const std::string &method, const std::vector<Need> &needs, bool known,
+                 int copy_tested)
+    {
+        if (method == "none") return true;
+        std::string missing;
+        if (method == "copy") {
+            if (!assoc(1, g, copy_tested)) missing = std::string(var) + " for surface_type=1 ";
+        } else if (method == "zero" && out_idx != FC_QSUR) {
+        } else if (known) {
+            for (const Need &n : needs)
+                if (!assoc(i, g, n.tested)) missing += std::string(" ") + n.label;
+        } else {
+            char buf[256];
+            snprintf(buf, sizeof buf, "Error calculating %s for surface_type %d on the grid %s: Method %s is not known.", var, i,
+                     g == 1 ? "t_grid" : (g == 2 ? "u_grid" : "v_grid"), method.c_str());
+            return stop(FC_ERR_METHOD, buf);
+        }
+        if (!rtrim(missing).empty() || (!missing.empty() && method == "copy")) {
+            char buf[512];
+            snprintf(buf, sizeof buf, "Error calculating %s for surface_type %d on the grid %s: For method %s we are lacking the following variables: %s",
+                     var, i, g == 1 ? "t_grid" : (g == 2 ? "u_grid" : "v_grid"), method.c_str(), rtrim(missing).c_str());
+            return stop(FC_ERR_MISSING, buf);
+        }
+        fc::SaSlot &o = slot(i, g, out_idx);      // do_prepare_calculation (prepare.F90:19-44)
+        if (method == "copy") {
+            o.arr = slot(1, g, out_idx).arr;
+        } else {
+            o.arr = new_array(g, 0.0, false);
+            o.allocated = true;
+        }
+        return true;
+    }
+
+    bool prepare_all(const std::vector<NmlValue> rg[4])
+    {
+        static const char *wnames[8] = {"which_spec_vapor_surface_t", "which_spec_vapor_surface_u", "which_spec_vapor_surface_v",
+                                        "which_flux_mass_evap", "which_flux_heat_latent", "which_flux_heat_sensible",
+                                        "which_flux_momentum", "which_flux_radiation_blackbody"};
+        std::vector<NmlValue> w[8];
+        for (int q = 0; q < 8; ++q) w[q] = get(wnames[q], {10, 10});
+        if (!err.empty()) return false;
+        auto meth = [&](int q, int i) {
+            const std::string s = str(w[q][(size_t)((m - 1) + 10 * (i - 1))], "none");
+            R.method[q][i] = s;
+            return s;
+        };
+        const int A = FC_AMOI, P = FC_PSUR, QA = FC_QATM, QS = FC_QSUR, TA = FC_TATM, TS = FC_TSUR, U = FC_UATM, V = FC_VATM;
+        for (int i = 1; i <= R.S; ++i)      // flux_calculator.F90:594-598
+            for (int g = 1; g <= 3; ++g) {
+                const std::string me = meth(g - 1, i);
+                if (!prepare("QSUR", FC_QSUR, i, g, me, {{FC_FICE, "FICE"}, {P, "PSUR"}, {TS, "TSUR"}}, me == "CCLM", FC_QSUR)) return false;
+            }
+        if (!prepare_regridding(FC_QSUR, 0, rg)) return false;
+        for (int i = 1; i <= R.S; ++i) {      // :603-605
+            const std::string me = meth(3, i);
+            std::vector<Need> n;
+            if (me == "CCLM") n = {{A, "AMOI"}, {P, "PSUR"}, {QA, "QATM"}, {QS, "QSUR"}, {TA, "TATM"}, {U, "UATM"}, {V, "VATM"}};
+            if (me == "MOM5") n = {{FC_CMOI, "CMOI"}, {P, "PSUR"}, {QA, "QATM"}, {QS, "QSUR"}, {TA, "TATM"}, {U, "UATM"}, {V, "VATM"}};
+            if (me == "RCO") n = {{QA, "QATM"}, {QS, "TSUR"}, {U, "UATM"}, {V, "VATM"}};      // prepare.F90:107 tests QSUR, says TSUR
+            if (!prepare("MEVA", FC_MEVA, i, 1, me, n, me == "CCLM" || me == "MOM5" || me == "RCO", FC_MEVA)) return false;
+        }
+        if (!prepare_regridding(FC_MEVA, 0, rg)) return false;
+        for (int i = 1; i <= R.S; ++i) {      // :610-612; 'copy' tests HSEN of type 1 (prepare.F90:132)
+            const std::string me = meth(4, i);
+            if (!prepare("HLAT", FC_HLAT, i, 1, me, {{FC_MEVA, "MEVA"}}, me == "water" || me == "ice", FC_HSEN)) return false;
+        }
+        if (!prepare_regridding(FC_HLAT, 0, rg)) return false;
+        for (int i = 1; i <= R.S; ++i) {      // :615-617; TATM is tested where the message says TSUR (prepare.F90:168,178,184)
+            const std::string me = meth(5, i);
+            std::vector<Need> n;
+            if (me == "CCLM") n = {{A, "AMOI"}, {FC_PATM, "PATM"}, {P, "PSUR"}, {QS, "QSUR"}, {TA, "TATM"}, {TA, "TSUR"}, {U, "UATM"}, {V, "VATM"}};
+            if (me == "MOM5") n = {{FC_CHEA, "CHEA"}, {FC_PATM, "PATM"}, {P, "PSUR"}, {QS, "QSUR"}, {TA, "TATM"}, {TA, "TSUR"}, {U, "UATM"}, {V, "VATM"}};
+            if (me == "RCO") n = {{TA, "TATM"}, {TA, "TSUR"}, {U, "UATM"}, {V, "VATM"}};
+            if (!prepare("HSEN", FC_HSEN, i, 1, me, n, me == "CCLM" || me == "MOM5" || me == "RCO", FC_HSEN)) return false;
+        }
+        if (!prepare_regridding(FC_HSEN, 0, rg)) return false;
+        for (int i = 1; i <= R.S; ++i) {      // :622-624
+            const std::string me = meth(7, i);
+            if (!prepare("RBBR", FC_RBBR, i, 1, me, {{TS, "TSUR"}}, me == "StBo", FC_RBBR)) return false;
+        }
+        if (!prepare_regridding(FC_RBBR, 0, rg)) return false;
+        for (int north = 0; north < 2; ++north) {      // :634-643; UATM is tested where the message of VMOM says VATM (prepare.F90:258,266)
+            const int g = north ? 3 : 2, out = north ? FC_VMOM : FC_UMOM;
+            const char *wl = north ? "VATM" : "UATM";
+            for (int i = 1; i <= R.S; ++i) {
+                const std::string me = meth(6, i);
+                std::vector<Need> n;
+                if (me == "CCLM") n = {{FC_AMOM, "AMOM"}, {P, "PSUR"}, {QS, "QSUR"}, {TA, "TATM"}, {TA, "TSUR"}, {U, wl}};
+                if (me == "MOM5") n = {{FC_CMOM, "CMOM"}, {P, "PSUR"}, {QS, "QSUR"}, {TA, "TATM"}, {TA, "TSUR"}, {U, wl}};
+                if (me == "RCO") n = {{U, "UATM"}, {V, "VATM"}};
+                if (!prepare(north ? "VMOM" : "UMOM", out, i, g, me, n, me == "CCLM" || me == "MOM5" || me == "RCO", out)) return false;
+            }
+            if (!prepare_regridding(out, 0, rg)) return false;
+        }
+        return true;
+    }
+
+    // add_output_field (basic.F90:170-283)
+    bool add_output(const std::string &name, char letter, int st, int g, bool uniform, double dflt)
+    {
+        char buf[16];
+        snprintf(buf, sizeof buf, "R%c%s%02d", letter, name.c_str(), st);
+        for (const fc::SaField &f : R.in)
+            if (f.name == buf) return true;      // comes in as an input: nothing to send (:195-199)
+        const int i = var_index(name);
+        if (!i) return stop(FC_ERR_ARG, "Could not add output field for variable " + name + " because flux_calculator does not know this variable.");
+        auto give_default = [&](int t) {
+            fc::SaSlot &s = slot(t, g, i);
+            s.arr = new_array(g, dflt, true);
+            s.allocated = true;
+            char w[160];
+            snprintf(w, sizeof w, "WARNING: Flux %s cannot be calculated for surface_type=%d => set to %g\n", name.c_str(), t, dflt);
+            R.warnings += w;
+        };
+        if (st == 0) {
+            if (uniform) {
+                for (int j = 1; j <= R.S; ++j)
+                    if (assoc(j, g, i) && !assoc(0, g, i)) slot(0, g, i).arr = slot(j, g, i).arr;      // pointer, not %allocated
+            } else {
+                bool fluxes = true, areas = true;
+                for (int j = 1; j <= R.S; ++j) {
+                    fluxes = fluxes && assoc(j, g, i);
+                    areas = areas && assoc(j, g, FC_FARE);
+                }
+                if (!areas)
+                    return stop(FC_ERR_MISSING, "ERROR: Output field " + name + " has not been defined as uniform (flux_?_uniform=.FALSE.). To calculate its "
+                                "average value across different surface_types, their fractional area (FARE) must be given but is missing.");
+                if (fluxes && !assoc(0, g, i)) {
+                    slot(0, g, i).arr = new_array(g, 0.0, false);
+                    slot(0, g, i).allocated = true;
+                }
+            }
+            if (!assoc(0, g, i)) give_default(0);
+        } else {
+            if (uniform && !assoc(st, g, i))
+                for (int j = 1; j <= R.S; ++j)
+                    if (assoc(j, g, i) && !assoc(0, g, i)) slot(0, g, i).arr = slot(j, g, i).arr;
+            if (!assoc(st, g, i)) give_default(st);
+        }
+        fc::SaField f;
+        snprintf(buf, sizeof buf, "S%c%s%02d", letter, name.c_str(), st);
+        f.name = buf;
+        f.grid = g;
+        f.type = st;
+        f.idx = i;
+        f.early = name == "RBBR" || name == "TSUR" || name == "FICE" || name == "ALBE";      // :271-273
+        R.out.push_back(f);
+        return true;
+    }
+
+    bool send_all()
+    {
+        std::vector<NmlValue> ns[3], sa[3], sb[3], su[3], vf[3];
+        static const char *sfx[3] = {"t", "u", "v"};
+        for (int g = 0; g < 3; ++g) {
+            const std::string s(sfx[g]);
+            ns[g] = get(("name_send_" + s).c_str(), {kMaxVarsNml});
+            sa[g] = get(("send_to_atmos_" + s).c_str(), {kMaxVarsNml});
+            sb[g] = get(("send_to_bottom_" + s).c_str(), {10, kMaxVarsNml});
+            su[g] = get(("send_uniform_" + s).c_str(), {10, kMaxVarsNml});
+            vf[g] = get(("val_flux_" + s).c_str(), {kMaxVarsNml});
+        }
+        if (!err.empty()) return false;
+        // the reference sizes output_field from this count (flux_calculator.F90:651-683) and then adds without checking:
+        // more additions than counted is an out-of-bounds write there, refused here
+        size_t counted = 0;
+        for (int g = 0; g < 3; ++g)
+            for (int j = 1; j <= kMaxVarsNml; ++j)
+                if (str(ns[g][(size_t)j - 1], "none") != "none")
+                    counted += flag(su[g][(size_t)((m - 1) + 10 * (j - 1))], false) ? 1 : (size_t)(1 + R.S);
+        for (int j = 1; j <= kMaxVarsNml; ++j)      // :690-761: t, u, v interleaved per j
+            for (int g = 0; g < 3; ++g) {
+                const std::string name = str(ns[g][(size_t)j - 1], "none");
+                if (name == "none") continue;
+                const bool to_atmos = flag(sa[g][(size_t)j - 1], true), to_bottom = flag(sb[g][(size_t)((m - 1) + 10 * (j - 1))], true);
+                const bool uni = flag(su[g][(size_t)((m - 1) + 10 * (j - 1))], false);
+                const double dflt = num(vf[g][(size_t)j - 1], 0.0);
+                if (to_atmos) {      // (on the t grid a flux that goes to the atmosphere only is never uniform, on u / v always: :697-700, :718-721)
+                    if (!add_output(name, 'A', 0, g + 1, to_bottom ? uni : (g != 0), dflt)) return false;
+                }
+                if (to_bottom) {
+                    if (uni) {
+                        if (!add_output(name, R.letter, 1, g + 1, true, dflt)) return false;
+                    } else {
+                        for (int i = 1; i <= R.S; ++i)
+                            if (!add_output(name, R.letter, i, g + 1, false, dflt)) return false;
+                    }
+                }
+            }
+        if (R.out.size() > counted)
+            return stop(FC_ERR_STATE, "the namelist sends more fields than the reference allocates room for (a uniform flux that goes to the atmosphere "
+                        "AND to the bottom model is counted once, flux_calculator.F90:655-660, but added twice, :694-712): undefined in the reference");
+        return true;
+    }
+
+    bool build(const int64_t grid_size[3])
+    {
+        for (int g = 0; g < 3; ++g) R.n[g + 1] = grid_size[g];
+        auto letters = get("letter_bottom_model", {10});
+        R.letter = 'M';
+        if (!letters.empty() && !letters[(size_t)m - 1].null && !letters[(size_t)m - 1].text.empty()) R.letter = letters[(size_t)m - 1].text[0];
+        // num_surface_types (:362-410): the highest surface type for which a bottom variable is named on any grid
+        R.S = 0;
+        for (const char *s : {"t", "u", "v"}) {
+            auto nb = get((std::string("name_bottom_var_") + s).c_str(), {10, 10, kMaxVarsNml});
+            if (!err.empty()) return false;
+            for (int i = 1; i <= 10; ++i)
+                for (int j = 1; j <= kMaxVarsNml; ++j)
+                    if (str(nb[(size_t)((m - 1) + 10 * (i - 1) + 100 * (j - 1))], "none") != "none") R.S = std::max(R.S, i);
+        }
+        if (R.S < 1) return stop(FC_ERR_ARG, "the namelist names no bottom-model variable for this bottom model: num_surface_types = 0");
+        if (!receive_grid(1, "t") || !receive_grid(2, "u") || !receive_grid(3, "v")) return false;
+        std::vector<NmlValue> rg[4] = {get("regrid_u_to_t", {10, 10, kMaxVarsNml}), get("regrid_v_to_t", {10, 10, kMaxVarsNml}),
+                                       get("regrid_t_to_u", {10, 10, kMaxVarsNml}), get("regrid_t_to_v", {10, 10, kMaxVarsNml})};
+        if (!err.empty()) return false;
+        const std::vector<fc::SaField> inputs = R.in;
+        for (const fc::SaField &f : inputs)      // STEP 1.5 (:575-578)
+            if (!prepare_regridding(f.idx, f.type, rg)) return false;
+        R.n_input_regrid = R.regrid.size();
+        if (!prepare_all(rg)) return false;      // STEP 1.6
+        return send_all();                       // STEP 1.7
+    }
+};
+
+bool parse_namelist_file(const char *path, std::vector<NmlGroup> &groups, std::string &err)
+{
+    std::string text;
+    if (!read_file(path, text)) {
+        err = std::string("cannot open namelist file ") + path;
+        return false;
+    }
+    NmlParser P(text);
+    if (!P.parse(groups)) {
+        err = std::string(path) + ": " + P.err;
+        return false;
+    }
+    return true;
+}
+
+std::string registry_json(const fc::Standalone &R)
+{
+    std::ostringstream o;
+    o << "{\"num_surface_types\":" << R.S << ",\"registry\":[";
+    bool first = true;
+    for (int i = 0; i <= 10; ++i)
+        for (int g = 1; g <= 3; ++g)
+            for (int k = 1; k <= FC_MAX_VARNAMES; ++k) {
+                const fc::SaSlot &s = R.slot[i][g][k];
+                if (s.arr < 0) continue;
+                const fc::SaArray &a = R.arrays[(size_t)s.arr];
+                o << (first ? "" : ",") << "{\"type\":" << i << ",\"grid\":" << g << ",\"var\":\"" << kNames35[k] << "\",\"storage\":" << s.arr
+                  << ",\"allocated\":" << (s.allocated ? "true" : "false") << ",\"fill\":";
+                if (a.has_fill) {
+                    char b[64];
+                    snprintf(b, sizeof b, "%.17g", a.fill);
+                    o << b;
+                } else {
+                    o << "null";
+                }
+                o << ",\"regrid_to\":[";
+                bool f2 = true;
+                for (int t = 1; t <= 3; ++t)
+                    if (s.put[t]) {
+                        o << (f2 ? "" : ",") << t;
+                        f2 = false;
+                    }
+                o << "]}";
+                first = false;
+            }
+    auto list = [&](const char *key, const std::vector<fc::SaField> &v) {
+        o << "],\"" << key << "\":[";
+        for (size_t k = 0; k < v.size(); ++k)
+            o << (k ? "," : "") << "{\"name\":\"" << v[k].name << "\",\"grid\":" << v[k].grid << ",\"early\":" << (v[k].early ? "true" : "false")
+              << ",\"type\":" << v[k].type << ",\"var\":\"" << kNames35[v[k].idx] << "\"}";
+    };
+    list("input_fields", R.in);
+    list("output_fields", R.out);
+    o << "]}";
+    return o.str();
+}
+
+}  // namespace
+
+// the registry the namelist describes, as JSON text (no device needed): what fc_create_from_namelist will build
+extern "C" int fc_namelist_registry(const char *nml_path, int bottom_model, const int64_t grid_size[3], char *out, int64_t outlen)
+{
+    if (!nml_path || !grid_size || !out || outlen < 2 || bottom_model < 1 || bottom_model > 10)
+        return fail(nullptr, FC_ERR_ARG, "fc_namelist_registry: bad argument");
+    std::vector<NmlGroup> groups;
+    std::string err;
+    if (!parse_namelist_file(nml_path, groups, err)) return fail(nullptr, FC_ERR_ARG, "%s", err.c_str());
+    fc::Standalone R;
+    SaBuilder B{R, groups, bottom_model};
+    if (!B.build(grid_size)) return fail(nullptr, B.err_code ? B.err_code : FC_ERR_ARG, "%s", B.err.c_str());
+    const std::string js = registry_json(R);
+    if ((int64_t)js.size() + 1 > outlen) return fail(nullptr, FC_ERR_NOMEM, "fc_namelist_registry: need %lld bytes", (long long)js.size() + 1);
+    memcpy(out, js.c_str(), js.size() + 1);
+    return FC_OK;
+}
+
+extern "C" int fc_create_from_namelist(fc_context **out, const char *nml_path, int bottom_model, const int64_t grid_size[3], int device)
+{
+    if (!out || !nml_path || !grid_size || bottom_model < 1 || bottom_model > 10)
+        return fail(nullptr, FC_ERR_ARG, "fc_create_from_namelist: bad argument");
+    std::vector<NmlGroup> groups;
+    std::string err;
+    if (!parse_namelist_file(nml_path, groups, err)) return fail(nullptr, FC_ERR_ARG, "%s", err.c_str());
+    std::unique_ptr<fc::Standalone> R(new fc::Standalone());
+    SaBuilder B{*R, groups, bottom_model};
+    if (!B.build(grid_size)) return fail(nullptr, B.err_code ? B.err_code : FC_ERR_ARG, "%s", B.err.c_str());
+    fc_context *c = nullptr;
+    if (int rc = fc_create(&c, grid_size, R->S, device)) return rc;
+    auto bail = [&](int rc) {
+        const std::string msg = c->err;
+        fc::standalone_free(*R);
+        fc_destroy(c);
+        return fail(nullptr, rc, "%s", msg.c_str());
+    };
+    // the arrays a Fortran host would ALLOCATE: page-locked, so that the per-step copies run at link speed
+    for (fc::SaArray &a : R->arrays) {
+        const int64_t n = std::max<int64_t>(R->n[a.grid], 1);
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, (size_t)n * sizeof(double), cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();
+            c->err = "fc_create_from_namelist: cudaHostAlloc failed";
+            return bail(FC_ERR_NOMEM);
+        }
+        a.host = (double *)p;
+        const double v = a.has_fill ? a.fill : nan("");      // what nobody has written yet reads as NaN, not as garbage
+        for (int64_t k = 0; k < n; ++k) a.host[k] = v;
+    }
+    for (int i = 0; i <= 10; ++i)
+        for (int g = 1; g <= 3; ++g)
+            for (int k = 1; k <= FC_MAX_VARNAMES; ++k) {
+                const fc::SaSlot &s = R->slot[i][g][k];
+                if (s.arr < 0 || i > R->S) continue;
+                if (int rc = fc_bind_field(c, i, g, k, R->arrays[(size_t)s.arr].host, R->n[g])) return bail(rc);
+                if (int rc = fc_set_allocated(c, i, g, k, s.allocated ? 1 : 0)) return bail(rc);
+                const fc::SaArray &a = R->arrays[(size_t)s.arr];
+                if (a.constant || (a.has_fill && !a.constant && false))
+                    if (int rc = fc_mark_static(c, i, g, k, 1)) return bail(rc);
+            }
+    static const char *wnames[8] = {"which_spec_vapor_surface_t", "which_spec_vapor_surface_u", "which_spec_vapor_surface_v",
+                                    "which_flux_mass_evap", "which_flux_heat_latent", "which_flux_heat_sensible",
+                                    "which_flux_momentum", "which_flux_radiation_blackbody"};
+    for (int q = 0; q < 8; ++q)
+        for (int i = 1; i <= R->S; ++i)
+            if (int rc = fc_set_method(c, wnames[q], i, R->method[q][i].c_str())) return bail(rc);
+    for (const fc::SaField &f : R->out)
+        if (int rc = fc_add_output_field(c, f.type, f.grid, f.idx)) return bail(rc);
+    c->warning = R->warnings;
+    c->sa = R.release();
+    if (int rc = fc_configure_from_namelist(c, nml_path, bottom_model)) {      // &correctionsctl (the methods are set already)
+        fc_context *dead = c;
+        const std::string msg = c->err;
+        fc_destroy(dead);
+        return fail(nullptr, rc, "%s", msg.c_str());
+    }
+    *out = c;
+    return FC_OK;
+}
+
+static int sa_field(fc_context *c, bool output, int j, char name[16], int *grid, int *early, int *surface_type, int *var_idx, double **field,
+                    int64_t *n)
+{
+    if (!c || !c->sa) return fail(c, FC_ERR_STATE, "this context was not created by fc_create_from_namelist");
+    const std::vector<fc::SaField> &v = output ? c->sa->out : c->sa->in;
+    if (j < 0 || j >= (int)v.size()) return fail(c, FC_ERR_ARG, "field number %d out of range 0..%d", j, (int)v.size() - 1);
+    const fc::SaField &f = v[(size_t)j];
+    if (name) snprintf(name, 16, "%s", f.name.c_str());
+    if (grid) *grid = f.grid;
+    if (early) *early = f.early ? 1 : 0;
+    if (surface_type) *surface_type = f.type;
+    if (var_idx) *var_idx = f.idx;
+    const fc::SaSlot &s = c->sa->slot[f.type][f.grid][f.idx];
+    if (field) *field = s.arr >= 0 ? c->sa->arrays[(size_t)s.arr].host : nullptr;
+    if (n) *n = c->sa->n[f.grid];
+    return FC_OK;
+}
+
+extern "C" int fc_num_input_fields(const fc_context *c) { return (c && c->sa) ? (int)c->sa->in.size() : -1; }
+extern "C" int fc_num_output_fields(const fc_context *c) { return (c && c->sa) ? (int)c->sa->out.size() : -1; }
+extern "C" int fc_input_field(fc_context *c, int j, char name[16], int *grid, int *early, int *surface_type, int *var_idx, double **field, int64_t *n)
+{
+    return sa_field(c, false, j, name, grid, early, surface_type, var_idx, field, n);
+}
+extern "C" int fc_output_field(fc_context *c, int j, char name[16], int *grid, int *early, int *surface_type, int *var_idx, double **field, int64_t *n)
+{
+    return sa_field(c, true, j, name, grid, early, surface_type, var_idx, field, n);
+}
+extern "C" int fc_field_pointer(fc_context *c, int surface_type, int grid, int var_idx, double **field, int64_t *n)
+{
+    if (!c || !c->sa) return fail(c, FC_ERR_STATE, "this context was not created by fc_create_from_namelist");
+    if (surface_type < 0 || surface_type > 10 || grid < 1 || grid > 3 || var_idx < 1 || var_idx > FC_MAX_VARNAMES || !field)
+        return fail(c, FC_ERR_ARG, "fc_field_pointer: bad argument");
+    const fc::SaSlot &s = c->sa->slot[surface_type][grid][var_idx];
+    *field = s.arr >= 0 ? c->sa->arrays[(size_t)s.arr].host : nullptr;
+    if (n) *n = c->sa->n[grid];
+    return FC_OK;
+}
+
+namespace fc {
+void standalone_free(Standalone &R)
+{
+    for (SaArray &a : R.arrays)
+        if (a.host) {
+            cudaFreeHost(a.host);
+            a.host = nullptr;
+        }
+}
+}  // namespace fc

@@ -161,6 +161,8 @@ struct FusedPlan {
     DiagFold fold_prev;      // rows of the previous specialised launch of the stream, folded by this launch (nslots == 0: none)
     int early_loads;         // the previous operation of the stream is this library's own step kernel (which writes no
                              // input): the producers may start their first bulk copies before griddepcontrol.wait
+    int dyn_min_tiles;       // dynamic schedule from this many tiles per CTA on (0: the built-in default)
+    int pad4;
     unsigned int tile_base;  // dynamic tile schedule of the specialised kernel without diagnostics: the counter's value
     unsigned int *tile_counter;   // before this launch (it is never reset, see spec_kernel.cu)
     double *diag_out;        // [sum|min|max][kDiagSlots] result of this step

@@ -56,6 +56,13 @@ constexpr int kSpecV = 2;
 #ifndef FC_SPEC2_TEAM_WARPS
 #define FC_SPEC2_TEAM_WARPS (16 / FC_SPEC2_TEAMS)
 #endif
+#ifndef FC_SPEC2_REGS
+#define FC_SPEC2_REGS 96            // two types: 17 warps.  One of the four SM sub-partitions (16384 registers each) holds five of them:
+#endif                              // 5 x 32 x 96 fits, 5 x 32 x 104 does not ("too many resources requested for launch" at 112 and 120)
+#ifndef FC_SPEC1_REGS
+#define FC_SPEC1_REGS 96            // one type: 2 CTAs x 9 warps per SM (112 would still fit the register file on paper, but measured
+                                    // 0.57 ms instead of 0.43 ms on C4: the second CTA no longer becomes resident)
+#endif
 #ifndef FC_SPEC_PAR_PRODUCER
 #define FC_SPEC_PAR_PRODUCER 0      // 0: lane 0 of the producer warp issues all bulk copies of a tile; 1: lane a issues slot a
 #endif
@@ -70,6 +77,8 @@ struct SpecGeom {
     static constexpr int kThreads = kConsumers + 32;         // + producer warp
     static constexpr int kWarps = kTeams * kTeamWarps;
     static constexpr int kCtasPerSm = (NS == 1) ? 2 : 1;
+    // registers per thread, stated directly (see the two macros above)
+    static constexpr int kMaxRegs = (NS == 1) ? FC_SPEC1_REGS : FC_SPEC2_REGS;
 };
 constexpr int kSpecMaxStages = 16;
 constexpr int kSpecMaxBars = 32;                         // barriers per set: lcm(teams, stages) <= 2 * 16
@@ -130,6 +139,8 @@ struct SpecPlan {
     int64_t rows, plane;
     DiagFold prev;                    // rows of the previous launch, folded here while the ring fills (nslots == 0: none)
     int early_loads;                  // first bulk copies before griddepcontrol.wait (previous kernel = own step)
+    int dyn;                          // this launch uses the dynamic schedule
+    int area_ahead;                   // fetch the cell areas one tile ahead (pays while the launch is latency bound: few tiles per CTA)
     unsigned int tile_base;           // dynamic schedule: value of *tile_counter before this launch's first claim
     unsigned int *tile_counter;       // dynamic schedule: tiles are claimed with atomicAdd (never reset: the host tracks the base)
     signed char dmap[(kSpecMaxNS + 1) * DQ_COUNT];   // type * DQ_COUNT + quantity -> compact diagnostics slot (-1: inactive)
@@ -695,12 +706,14 @@ __device__ __noinline__ void spec_cold_phase(const SpecPlan &p, int ph, int64_t 
 // two ring carvings need no change) and hand the tile number to the consumers through shared memory, published by
 // the same mbarrier phase that publishes the tile's bytes.  A phase ends with one sentinel per team.  Partial tiles
 // are claimed like all others and read straight from global memory.  The counter is never reset: every producer
-// makes exactly one failing claim, so a launch advances it by (tiles + CTAs) and the host keeps the base.
-// (With diagnostics the per-thread running sums need a reproducible tile -> thread map: static schedule.)
+// makes exactly two failing claims (two are kept in flight), so a launch advances it by (units + 2 CTAs) and the host
+// keeps the base.  Small grids (few tiles per CTA: nothing to balance, and the claims' latency shows) and launches
+// with diagnostics (the per-thread running sums need a reproducible tile -> thread map) use the static schedule.
 #ifndef FC_SPEC_DYNAMIC
 #define FC_SPEC_DYNAMIC 1
 #endif
 constexpr int kDynPartial = 1 << 30;      // tile id flag: partial tile, nothing in the stage
+constexpr unsigned kDynUvBatch = 4;       // u/v tiles per claim
 
 template <int SET, int NS>
 __device__ __noinline__ void spec_cold_dyn(const SpecPlan &p, int uv, const int *ids, int n, int ttid)
@@ -724,14 +737,22 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
     const int NT = p.t_stages, NUS = p.u_stages, LT = p.t_bars, LU = p.u_bars;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned nt0 = (unsigned)p.ntiles[0], nt1 = (unsigned)p.ntiles[1], nt2 = (unsigned)p.ntiles[2];
-    const unsigned total = nt0 + nt1 + nt2;
     const bool partial[3] = {(p.end[0] - p.first[0]) % GEO::kTile != 0, (p.end[1] - p.first[1]) % GEO::kTile != 0,
                              (p.end[2] - p.first[2]) % GEO::kTile != 0};
 
     if (warp == GEO::kWarps) {
         // ---------------- producer: one lane claims, publishes and fetches ----------------
         if (lane != 0) return;
+        // work units: unit u < nt0 is t tile u; unit nt0 + q is the kDynUvBatch consecutive tiles 4q .. 4q+3 of the list
+        // [u tiles | v tiles] (they are light: a claim per tile would cost more than the tile).  Two claims are kept in
+        // flight so that the atomic's round trip overlaps the issue of the previous unit's copies.
+        const unsigned nuv = nt1 + nt2, units = nt0 + (nuv + kDynUvBatch - 1) / kDynUvBatch;
         unsigned g = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+        unsigned g_ahead = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+        auto claim = [&]() {      // unconditional: every producer ends with exactly two failing claims, whatever it got before
+            g = g_ahead;
+            g_ahead = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+        };
         int i = 0;
         {   // t tiles: local tile i -> stage i mod NT, barrier i mod LT
             int st = 0, bi = 0, pb = 0, puse = 0;
@@ -764,7 +785,7 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
                         if (p.src[0][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[0][a] + cell, GEO::kSlotBytes, &fullT[bi]);
                 }
                 next();
-                g = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+                claim();
             }
             const int ring0 = i;      // t tiles this CTA took
             for (int t = 0; t < TEAMS; ++t) {      // end of the t phase, once per team
@@ -799,24 +820,27 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
                 if (++bi == LU) bi = 0;
                 ++k;
             };
-            while (g < total) {
-                const int ph = g < nt0 + nt1 ? 1 : 2;
-                const unsigned tile = g - (ph == 1 ? nt0 : nt0 + nt1);
-                slot();
-                const bool part = partial[ph] && tile == (ph == 1 ? nt1 : nt2) - 1;
-                tileU[bi] = (int)((tile << 1) | (unsigned)(ph - 1)) | (part ? kDynPartial : 0);
-                if (part) {
-                    mbar_arrive(&fullU[bi]);
-                } else {
-                    const int64_t cell = p.first[ph] + (int64_t)tile * GEO::kTile;
-                    mbar_expect_tx(&fullU[bi], p.tx_bytes[ph]);
-                    char *dst = ring + (size_t)st * p.u_stage_bytes;
+            while (g < units) {
+                const unsigned w0 = (g - nt0) * kDynUvBatch, w1 = (w0 + kDynUvBatch < nuv) ? w0 + kDynUvBatch : nuv;
+                for (unsigned w = w0; w < w1; ++w) {
+                    const int ph = w < nt1 ? 1 : 2;
+                    const unsigned tile = ph == 1 ? w : w - nt1;
+                    slot();
+                    const bool part = partial[ph] && tile == (ph == 1 ? nt1 : nt2) - 1;
+                    tileU[bi] = (int)((tile << 1) | (unsigned)(ph - 1)) | (part ? kDynPartial : 0);
+                    if (part) {
+                        mbar_arrive(&fullU[bi]);
+                    } else {
+                        const int64_t cell = p.first[ph] + (int64_t)tile * GEO::kTile;
+                        mbar_expect_tx(&fullU[bi], p.tx_bytes[ph]);
+                        char *dst = ring + (size_t)st * p.u_stage_bytes;
 #pragma unroll 1
-                    for (int a = 0; a < L::NUV; ++a)
-                        if (p.src[ph][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[ph][a] + cell, GEO::kSlotBytes, &fullU[bi]);
+                        for (int a = 0; a < L::NUV; ++a)
+                            if (p.src[ph][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[ph][a] + cell, GEO::kSlotBytes, &fullU[bi]);
+                    }
+                    next();
                 }
-                next();
-                g = atomicAdd(p.tile_counter, 1u) - p.tile_base;
+                claim();
             }
             for (int t = 0; t < TEAMS; ++t) {      // end of the step, once per team
                 slot();
@@ -903,7 +927,7 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
 // the kernel
 // ---------------------------------------------------------------------------------------------
 template <int SET, int NS, int DIAG>
-__global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPerSm) flux_spec_kernel(const __grid_constant__ SpecPlan p)
+__global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<NS>::kMaxRegs) flux_spec_kernel(const __grid_constant__ SpecPlan p)
 {
     using GEO = SpecGeom<NS>;
     constexpr int TEAMS = GEO::kTeams;
@@ -914,7 +938,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     __shared__ uint64_t fullT[kSpecMaxBars], emptyT[kSpecMaxBars], fullU[kSpecMaxBars], emptyU[kSpecMaxBars];
     __shared__ int flagged[GEO::kWarps][kSpecBadCap];
     __shared__ int nflagged[GEO::kWarps];
-    constexpr bool DYN = (DIAG == 0) && FC_SPEC_DYNAMIC;
+    constexpr bool DYN = (DIAG == 0) && FC_SPEC_DYNAMIC;      // instantiations that carry the dynamic schedule (chosen per launch: p.dyn)
     __shared__ int tileT[DYN ? kSpecMaxBars : 1], tileU[DYN ? kSpecMaxBars : 1];      // dynamic schedule: tile of each barrier slot
     __shared__ WarpSums<NS, DIAG> ws;
     __shared__ double wacc[(NS > 1 && DIAG) ? GEO::kWarps : 1][(NS > 1 && DIAG) ? (DIAG >= 2 ? 3 : 1) * kDiagAccMax : 1];
@@ -950,8 +974,10 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
     const bool early_producer = p.early_loads && (threadIdx.x >> 5) == GEO::kWarps;
     if (!early_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
     if constexpr (DYN) {      // (its producer never has to wait: it reads input arrays and the tile counter only)
-        spec_dynamic_body<SET, NS>(p, ring, fullT, emptyT, fullU, emptyU, tileT, tileU, flagged, nflagged);
-        return;
+        if (p.dyn) {
+            spec_dynamic_body<SET, NS>(p, ring, fullT, emptyT, fullU, emptyU, tileT, tileU, flagged, nflagged);
+            return;
+        }
     }
 
     // static schedule: this CTA takes positions b, b+G, b+2G, ... of the tile list [t tiles | u tiles | v tiles]
@@ -1100,12 +1126,14 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
         // the cell areas do not travel through the ring: each thread fetches its 16 bytes ONE TILE AHEAD, so that the
         // load's latency hides behind the chain of the current tile instead of in front of it
         double2 a_next = make_double2(0.0, 0.0);
-        if (DIAG && team < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
+        const int64_t ahead = p.area_ahead ? TEAMS * jstride : 0;
+        if (DIAG && p.area_ahead && team < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
         for (int i = team; i < ring0; i += TEAMS, j += TEAMS * jstride, ++mine) {
             if (DIAG) {
+                if (!p.area_ahead) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j));
                 dg.area.v[0] = a_next.x;
                 dg.area.v[1] = a_next.y;
-                if (i + TEAMS < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j + TEAMS * jstride));
+                if (p.area_ahead && i + TEAMS < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j + ahead));
             }
             mbar_wait(&fullT[bi], use & 1);
             FastVec<kSpecV> m;
@@ -1175,12 +1203,14 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads, SpecGeom<NS>::kCtasPer
             const int64_t jfirst = jbase + (int64_t)i0 * jstride;
             int64_t j = jfirst;
             double2 a_next = make_double2(0.0, 0.0);
-            if (DIAG && i0 < ring_ph) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
+            const int64_t ahead = p.area_ahead ? TEAMS * jstride : 0;
+            if (DIAG && p.area_ahead && i0 < ring_ph) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
             for (int i = i0; i < ring_ph; i += TEAMS, j += TEAMS * jstride, ++mine) {
                 if (DIAG) {
+                    if (!p.area_ahead) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j));
                     dg.area.v[0] = a_next.x;
                     dg.area.v[1] = a_next.y;
-                    if (i + TEAMS < ring_ph) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j + TEAMS * jstride));
+                    if (p.area_ahead && i + TEAMS < ring_ph) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[ph] + j + ahead));
                 }
                 mbar_wait(&fullU[bi], use & 1);
                 FastVec<kSpecV> m;
@@ -1411,6 +1441,7 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     sp.prev = p.fold_prev;
     sp.tile_counter = p.tile_counter;
     sp.tile_base = p.tile_base;
+    sp.dyn = p.dyn_min_tiles;
     sp.early_loads = p.early_loads;
     *set_out = set;
     return true;
@@ -1439,13 +1470,25 @@ int spec_applicable(const FusedPlan &p, const int64_t first[3], const int64_t ce
 
 // dynamic schedule: by how much a launch of this plan advances the tile counter (every tile is claimed once, every CTA's
 // producer makes one failing claim); 0: the plan runs on the static schedule
+// tiles per CTA from which the dynamic schedule is used: below, the static one has nothing to lose to imbalance and the
+// claims would only add latency (measured, RCO set at 10^6 cells = 20 tiles per CTA: 29.2 us static, 32.7 us dynamic)
+#ifndef FC_SPEC_DYN_MIN_TILES
+#define FC_SPEC_DYN_MIN_TILES 48
+#endif
+static bool spec_wants_dyn(const SpecPlan &sp)
+{
+    if (!FC_SPEC_DYNAMIC || sp.diag) return false;
+    const int64_t min_tiles = sp.dyn > 0 ? sp.dyn : FC_SPEC_DYN_MIN_TILES;      // (before the launch sp.dyn carries the caller's threshold)
+    return (int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] >= min_tiles * spec_grid(sp);
+}
+
 unsigned int spec_dyn_claims(const FusedPlan &p, const int64_t first[3], const int64_t cells[3])
 {
-    if (!FC_SPEC_DYNAMIC || p.diag) return 0;
     SpecPlan sp;
     int set = 0;
-    if (cells[0] + cells[1] + cells[2] <= 0 || !spec_build(p, first, cells, sp, &set)) return 0;
-    return (unsigned int)(sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] + spec_grid(sp));
+    if (cells[0] + cells[1] + cells[2] <= 0 || !spec_build(p, first, cells, sp, &set) || !spec_wants_dyn(sp)) return 0;
+    const unsigned nuv = (unsigned)(sp.ntiles[1] + sp.ntiles[2]);
+    return (unsigned int)sp.ntiles[0] + (nuv + kDynUvBatch - 1) / kDynUvBatch + 2u * (unsigned)spec_grid(sp);
 }
 
 template <int SET, int NS, int DIAG>
@@ -1491,8 +1534,12 @@ int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[
     int set = 0;
     if (!spec_build(p, first, cells, sp, &set)) return (int)cudaErrorInvalidValue;
     if (sp.diag && !sp.partials) return (int)cudaErrorInvalidValue;
-    if (!sp.diag && FC_SPEC_DYNAMIC && !sp.tile_counter) return (int)cudaErrorInvalidValue;
     const int grid = spec_grid(sp);
+    sp.dyn = spec_wants_dyn(sp) ? 1 : 0;
+    if (sp.dyn && !sp.tile_counter) return (int)cudaErrorInvalidValue;
+    // cell areas one tile ahead while there are few tiles per CTA (8-GPU shard of C4, 25 tiles per CTA: 61.3 -> 58.3 us);
+    // with many the kernel is DRAM bound and the earlier loads only synchronise the warps (10^7 cells: 0.433 -> 0.455 ms)
+    sp.area_ahead = ((int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] < (int64_t)64 * grid) ? 1 : 0;
     cudaError_t e;
     if (set == SET_BULK) e = (sp.ns == 1) ? spec_launch_d<SET_BULK, 1>(sp, grid, stream) : spec_launch_d<SET_BULK, 2>(sp, grid, stream);
     else e = (sp.ns == 1) ? spec_launch_d<SET_RCO, 1>(sp, grid, stream) : spec_launch_d<SET_RCO, 2>(sp, grid, stream);

@@ -59,6 +59,18 @@ class FluxCalculator:
         self._check(lib.fc_bind_field(self._ctx, surface_type, grid, idx, ptr, n))
         self._keep[(surface_type, grid, idx)] = array
 
+    def set_allocated(self, surface_type, grid, var, allocated):
+        """local_field(surface_type, grid)%var(idx_<var>)%allocated as the host's registry has it (None: infer)"""
+        self._check(lib.fc_set_allocated(self._ctx, surface_type, grid, var_index(var),
+                                         -1 if allocated is None else int(bool(allocated))))
+
+    def mark_static(self, surface_type, grid, var, is_static=True):
+        """the host does not rewrite this bound array between steps (a namelist constant): uploaded once"""
+        self._check(lib.fc_mark_static(self._ctx, surface_type, grid, var_index(var), int(bool(is_static))))
+
+    def mark_dirty(self, surface_type, grid, var):
+        self._check(lib.fc_mark_dirty(self._ctx, surface_type, grid, var_index(var)))
+
     def field(self, surface_type, grid, var):
         return self._keep.get((surface_type, grid, var_index(var)))
 
@@ -214,6 +226,53 @@ class FluxCalculator:
         dp = dst.ptr if isinstance(dst, DeviceArray) else dst.ctypes.data
         sp = src.ptr if isinstance(src, DeviceArray) else src.ctypes.data
         self._check(lib.fc_regrid(self._ctx, direction, dp, sp))
+
+
+def namelist_registry(nml_path, bottom_model, grid_size):
+    """the registry flux_calculator.nml describes (what fc_create_from_namelist builds), parsed from the library's JSON text"""
+    import json
+    gs = (C.c_int64 * 3)(*[int(x) for x in grid_size])
+    buf = C.create_string_buffer(1 << 22)
+    check(lib.fc_namelist_registry(str(nml_path).encode(), int(bottom_model), gs, buf, len(buf)))
+    return json.loads(buf.value.decode())
+
+
+class NamelistCalculator(FluxCalculator):
+    """a FluxCalculator whose registry, methods and field lists come from a flux_calculator.nml (fc_create_from_namelist):
+    the library owns the host arrays; `inputs` / `outputs` list (name, grid, early, surface type, variable, NumPy view)"""
+
+    def __init__(self, nml_path, grid_size, bottom_model=1, device=0):
+        gs = (C.c_int64 * 3)(*[int(x) for x in grid_size])
+        self._ctx = C.c_void_p()
+        check(lib.fc_create_from_namelist(C.byref(self._ctx), str(nml_path).encode(), int(bottom_model), gs, int(device)))
+        self.grid_size = tuple(int(x) for x in grid_size)
+        self.device = int(device)
+        self._keep, self._misc = {}, []
+        self.inputs = self._fields(lib.fc_num_input_fields, lib.fc_input_field)
+        self.outputs = self._fields(lib.fc_num_output_fields, lib.fc_output_field)
+        self.num_surface_types = max([f["type"] for f in self.inputs + self.outputs] + [1])
+
+    def _fields(self, count, getter):
+        res = []
+        for j in range(count(self._ctx)):
+            name = C.create_string_buffer(16)
+            g, e, t, v = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+            p, n = C.c_void_p(), C.c_int64()
+            self._check(getter(self._ctx, j, name, C.byref(g), C.byref(e), C.byref(t), C.byref(v), C.byref(p), C.byref(n)))
+            res.append({"name": name.value.decode(), "grid": g.value, "early": bool(e.value), "type": t.value, "var": VARNAMES[v.value - 1],
+                        "array": self._view(p.value, n.value)})
+        return res
+
+    @staticmethod
+    def _view(ptr, n):
+        if not ptr or n <= 0:
+            return np.empty(0)
+        return np.frombuffer((C.c_double * n).from_address(ptr), dtype=np.float64, count=n)
+
+    def array(self, surface_type, grid, var):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(lib.fc_field_pointer(self._ctx, surface_type, grid, var_index(var), C.byref(p), C.byref(n)))
+        return self._view(p.value, n.value) if p.value else None
 
 
 def namelist_get(nml_path, group, name, shape=(), index=()):

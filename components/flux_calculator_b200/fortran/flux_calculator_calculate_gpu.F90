@@ -46,6 +46,9 @@ MODULE flux_calculator_calculate
                     IF (ASSOCIATED(local_field(i,g)%var(k)%field)) THEN
                         CALL fc_check(ctx, fc_bind_field(ctx, INT(i, c_int), INT(g, c_int), INT(k, c_int),         &
                                       c_loc(local_field(i,g)%var(k)%field), INT(grid_size(g), c_int64_t)), 'fc_bind_field')
+                        ! the flag average_across_surface_types tests (flux_calculator_calculate.F90:376), as the registry has it
+                        CALL fc_check(ctx, fc_set_allocated(ctx, INT(i, c_int), INT(g, c_int), INT(k, c_int),      &
+                                      MERGE(1_c_int, 0_c_int, local_field(i,g)%var(k)%allocated)), 'fc_set_allocated')
                     ENDIF
                 ENDDO
             ENDDO

@@ -161,7 +161,8 @@ module fluxcalc_c_api
       character(kind=c_char), intent(in) :: nml_path(*)      ! NUL-terminated
       integer(c_int), value :: bottom_model
     end function
-    integer(c_int) function fc_load_corrections(ctx, root_dir, grid_offset, reference_start_quirk) bind(c, name='fc_load_corrections')
+    integer(c_int) function fc_load_corrections(ctx, root_dir, grid_offset, reference_start_quirk) &
+        bind(c, name='fc_load_corrections')
       import :: c_ptr, c_int, c_int64_t, c_char
       type(c_ptr), value :: ctx
       character(kind=c_char), intent(in) :: root_dir(*)      ! NUL-terminated; contains corrections/
@@ -196,25 +197,52 @@ module fluxcalc_c_api
       integer(c_int), value :: rank, nranks
       integer(c_int64_t), intent(out) :: offset, size
     end function
-    ! ---- Level 1 (array forms of the flux_lib routines); shown for two, the others follow the same pattern ----
-    integer(c_int) function fc_flux_mass_evap_cclm(flux_mass_evap, diffusion_coefficient_moisture, pressure_surface, &
-        specific_vapor_content_atmos, specific_vapor_content_surface, temperature_surface, u_atmos, v_atmos, n, &
-        u_min_evap_new, gas_constant_air_new, gas_constant_vapor_new, stream) bind(c, name='fc_flux_mass_evap_cclm')
-      import :: c_ptr, c_int, c_int64_t
-      type(c_ptr), value :: flux_mass_evap, diffusion_coefficient_moisture, pressure_surface, &
-                            specific_vapor_content_atmos, specific_vapor_content_surface, temperature_surface, &
-                            u_atmos, v_atmos
-      integer(c_int64_t), value :: n
-      type(c_ptr), value :: u_min_evap_new, gas_constant_air_new, gas_constant_vapor_new   ! c_null_ptr = not PRESENT
-      type(c_ptr), value :: stream
+    ! %allocated of a registry slot as the host has it (flux_calculator_basic.F90:88); -1 = infer from the aliasing
+    integer(c_int) function fc_set_allocated(ctx, surface_type, grid, var_idx, allocated) bind(c, name='fc_set_allocated')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: surface_type, grid, var_idx, allocated
     end function
-    integer(c_int) function fc_flux_radiation_blackbody_StBo(flux_radiation_blackbody, temperature_surface, n, &
-        stefan_boltzmann_constant_new, stream) bind(c, name='fc_flux_radiation_blackbody_StBo')
-      import :: c_ptr, c_int, c_int64_t
-      type(c_ptr), value :: flux_radiation_blackbody, temperature_surface
-      integer(c_int64_t), value :: n
-      type(c_ptr), value :: stefan_boltzmann_constant_new, stream
+    ! host-pointer mode: what does not have to cross PCIe every step (namelist constants val_*, flux_calculator.F90:444-449)
+    integer(c_int) function fc_mark_static(ctx, surface_type, grid, var_idx, is_static) bind(c, name='fc_mark_static')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: surface_type, grid, var_idx, is_static
     end function
+    integer(c_int) function fc_mark_dirty(ctx, surface_type, grid, var_idx) bind(c, name='fc_mark_dirty')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: surface_type, grid, var_idx
+    end function
+    integer(c_int) function fc_bind_thread_to_device_numa(device) bind(c, name='fc_bind_thread_to_device_numa')
+      import :: c_int
+      integer(c_int), value :: device
+    end function
+    ! nsteps consecutive coupling steps without host synchronisation (device-resident fields; CUDA graph per month)
+    integer(c_int) function fc_run_steps(ctx, t0, timestep, nsteps) bind(c, name='fc_run_steps')
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int64_t), value :: t0, timestep
+      integer(c_int), value :: nsteps
+    end function
+    ! do_regridding (flux_calculator_basic.F90:463-522): direction 0 = u->t, 1 = v->t, 2 = t->u, 3 = t->v; 1-based indices
+    integer(c_int) function fc_set_regrid_matrix(ctx, direction, num_elements, src_index, dst_index, weight) &
+        bind(c, name='fc_set_regrid_matrix')
+      import :: c_ptr, c_int, c_int64_t
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: direction
+      integer(c_int64_t), value :: num_elements
+      type(c_ptr), value :: src_index, dst_index, weight     ! c_loc(matrix%src_index%field) ... (integer(4), real(8))
+    end function
+    integer(c_int) function fc_regrid(ctx, direction, dst, src) bind(c, name='fc_regrid')
+      import :: c_ptr, c_int
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: direction
+      type(c_ptr), value :: dst, src
+    end function
+    ! ---- Level 1: the 14 array routines are declared in the GENERATED module fluxcalc_level1_api
+    !      (fluxcalc_level1_api.F90, written by gen_fortran_api.py from include/fluxcalc.h); MODULE flux_library with the
+    !      reference's public names on top of them is flux_library_gpu.F90 ----
   end interface
 
 contains

@@ -185,6 +185,23 @@ int fc_destroy(fc_context *ctx);
  * condition average_across_surface_types tests, calculate.F90:376) iff no slot of a surface type >= 1
  * is bound to the same p.  p == NULL unbinds (NULLIFY).  n must equal grid_size[grid-1]. */
 int fc_bind_field(fc_context *ctx, int surface_type, int grid, int var_idx, double *p, int64_t n);
+/* local_field(surface_type, grid)%var(var_idx)%allocated (flux_calculator_basic.F90:88), the flag
+ * average_across_surface_types tests (calculate.F90:376): 1 / 0 as the host's registry has it (set by allocate_localvar
+ * basic.F90:299, do_prepare_calculation prepare.F90:41, add_output_field basic.F90:226,239,259; NOT set for pointer
+ * aliases), -1 = infer from the aliasing as described above (the default).  The Fortran shim passes the real flag. */
+int fc_set_allocated(fc_context *ctx, int surface_type, int grid, int var_idx, int allocated);
+
+/* Host-pointer mode moves every bound array across PCIe every step unless told otherwise:
+ *   fc_mark_static : the host will not rewrite this array between steps (the reference's own idiom: fields given as a
+ *                    constant in the namelist, val_bottom_var_* / val_atmos_var_*, flux_calculator.F90:444-449, are
+ *                    written once by init_localvar) -> uploaded once;  fc_mark_dirty: ... it did change, upload it again.
+ *   option "download" = 1 : only fields registered with fc_add_output_field come back (what the reference hands to
+ *                    oasis_put); intermediates such as QSUR stay on the device. */
+int fc_mark_static(fc_context *ctx, int surface_type, int grid, int var_idx, int is_static);
+int fc_mark_dirty(fc_context *ctx, int surface_type, int grid, int var_idx);
+/* pins the calling thread to the CPUs next to `device` (sysfs local_cpulist of its PCI function), so that host buffers
+ * allocated afterwards are local to the GPU's socket; one rank per GPU calls it before allocating its fields */
+int fc_bind_thread_to_device_numa(int device);
 
 /* Method string of one namelist array for one surface type (flux_calculator.F90:99-107):
  *   which = "which_spec_vapor_surface_t" | "_u" | "_v"  : none copy CCLM
@@ -243,8 +260,12 @@ int fc_average_across_surface_types(fc_context *ctx, int which_grid, int var_idx
 int fc_step_early(fc_context *ctx, int64_t current_step_time);
 int fc_step_normal(fc_context *ctx, int64_t current_step_time);
 int fc_step_all(fc_context *ctx, int64_t current_step_time);
-/* nsteps consecutive fc_step_all at t0, t0+dt, ... without host synchronisation in between
- * (device-resident fields only; launch sequence is captured in a CUDA graph per month) */
+/* nsteps consecutive fc_step_all at t0, t0+dt, ... without host synchronisation in between (device-resident fields
+ * only) -- the time loop of flux_calculator.F90:859-1028 for a host that keeps its fields on the device.  The steps of one
+ * calendar month differ in nothing (the month selects the bias slab, calculate.F90:66-73): they are issued as replays of
+ * one CUDA graph of 32 step launches per month, the remainder directly.  Results are bit-identical to nsteps calls of
+ * fc_step_all.  With diagnostics only the LAST step's values can be read afterwards.  Option "graphs" = 0 issues
+ * every step directly. */
 int fc_run_steps(fc_context *ctx, int64_t t0, int64_t timestep, int nsteps);
 
 int fc_synchronize(fc_context *ctx);
@@ -259,7 +280,12 @@ int fc_event_record(fc_context *ctx, int which);
 int fc_event_elapsed_ms(fc_context *ctx, double *ms);
 int fc_kernel_time_ms(fc_context *ctx, double *total_ms, int64_t *count);
 
-/* options: "force_generic" (0/1: use the op-list interpreter kernels instead of the fused kernel),
+/* options: "early_loads" (0/1, default 1: a step that directly follows another step of this context on its stream may
+ *          fill its shared-memory ring before the previous step has finished -- steps write no input array; set
+ *          "stream_touched" = 1 after enqueuing own work that writes bound arrays on fc_get_stream()),
+ *          "graphs" (0/1, default 1: fc_run_steps replays CUDA graphs), "dyn_min_tiles" (tiles per CTA from which the
+ *          specialised kernel without diagnostics claims tiles dynamically; 0 = default 48),
+ *          "force_generic" (0/1: use the op-list interpreter kernels instead of the fused kernel),
  *          "pin_host" (0/1: cudaHostRegister bound host arrays), "h2d_chunks" (pipeline depth of the
  *          host-pointer path), "diagnostics" (0 off, 1 area-weighted sums, 2 sums + min/max),
  *          "profile_kernel" (0 off, n: time every n-th fused launch), "staged" (specialised persistent kernel: 0 never,
@@ -316,6 +342,32 @@ int fc_regrid(fc_context *ctx, int direction, double *dst, const double *src);
  * lcorrections(1) (bias_corrections.F90:60-76) for fc_load_corrections.  Standard Fortran namelist input: comments,
  * r*c repeats, null values, element / section subscripts, array element order. */
 int fc_configure_from_namelist(fc_context *ctx, const char *nml_path, int bottom_model);
+/* The WHOLE &input group drives a context: what the reference's main program does between reading the namelist and the
+ * time loop (flux_calculator.F90 STEP 1.4-1.7, :340-768, with allocate_localvar / init_localvar / distribute_input_field /
+ * add_input_field / add_output_field / prepare_regridding of flux_calculator_basic.F90 and the prepare_* routines of
+ * flux_calculator_prepare.F90, required-input quirks and error messages included).  The context owns the (page-locked)
+ * host arrays a Fortran host would ALLOCATE; val_* constants are written once and marked static; 'copy' methods, uniform
+ * outputs and the distribution of atmosphere fields over the surface types are pointer aliases; the %allocated flags, the
+ * OASIS names (R/S + model letter + variable + surface type), the early flags and the regridding requests
+ * (regrid_t_to_u ...) are the reference's.  A namelist the reference would stop on returns its message (FC_ERR_MISSING,
+ * FC_ERR_METHOD); one it would run into undefined behaviour with (more sent fields than it allocates room for) is refused.
+ * The host then fills the received fields (fc_input_field), sets regridding matrices if the namelist asks for any
+ * (fc_set_regrid_matrix) and steps: fc_step_early / fc_step_normal regrid the received fields of their phase first
+ * (do_regridding, flux_calculator.F90:891-896, :961-966) and computed ones after their calculator (:975-989). */
+int fc_create_from_namelist(fc_context **ctx, const char *nml_path, int bottom_model, const int64_t grid_size[3], int device);
+int fc_num_input_fields(const fc_context *ctx);       /* -1 unless created from a namelist */
+int fc_num_output_fields(const fc_context *ctx);
+/* field j (0-based, the reference's order): OASIS name (<= 8 characters + NUL), grid, early flag, surface type, variable
+ * index, the bound host array and its length; any out pointer may be NULL */
+int fc_input_field(fc_context *ctx, int j, char name[16], int *grid, int *early, int *surface_type, int *var_idx, double **field,
+                   int64_t *n);
+int fc_output_field(fc_context *ctx, int j, char name[16], int *grid, int *early, int *surface_type, int *var_idx, double **field,
+                    int64_t *n);
+int fc_field_pointer(fc_context *ctx, int surface_type, int grid, int var_idx, double **field, int64_t *n);
+/* the registry that namelist describes as JSON text (no device needed): slots with storage group, %allocated, constant,
+ * regridding flags; input and output field lists */
+int fc_namelist_registry(const char *nml_path, int bottom_model, const int64_t grid_size[3], char *out, int64_t outlen);
+
 /* initialize_bias_corrections (bias_corrections.F90:165-249): if lcorrections is set, reads variable 'mass_evap' of
  * <root_dir>/corrections/mass_evap-01.nc ... -12.nc (NetCDF classic CDF-1/2/5), cells [grid_offset, grid_offset + n_t),
  * replaces _FillValue by 0 and hands the (1,12,n_t) array to fc_set_corrections.  A month whose file, variable or

@@ -14,7 +14,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 import components.flux_calculator_b200 as m  # noqa: E402
 from components.flux_calculator_b200 import DeviceArray  # noqa: E402
-from components.flux_calculator_b200.synthetic import Scenario  # noqa: E402
+from synthetic import Scenario  # noqa: E402
 from oracle_py import Oracle, ulp_diff  # noqa: E402
 from tolerances import K_ULP, ULP, Scales  # noqa: E402
 

@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
 import numpy as np
 import components.flux_calculator_b200 as m
-from components.flux_calculator_b200.synthetic import Scenario
+from synthetic import Scenario
 from oracle_py import Oracle
 from tolerances import check_field
 fset, staged, n = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])

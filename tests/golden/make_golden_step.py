@@ -197,6 +197,9 @@ class Reference:
                     gid = groups.setdefault(id(arr), len(groups))
                     out.append({"type": i, "grid": g, "var": names[k], "storage": gid, "allocated": bool(v.c["allocated"]),
                                 "values": [hx(x) for x in arr.data]})
+                    for tg, comp in ((1, "put_to_t_grid"), (2, "put_to_u_grid"), (3, "put_to_v_grid")):
+                        if v.c[comp] is True:
+                            out[-1].setdefault("regrid_to", []).append(tg)
         return out
 
     def io_lists(self):
@@ -512,7 +515,8 @@ def run_scenario(ref, sd, seed):
             R.set_matrix(which, src, dst, w)
             mats[which] = {"src_index": src, "dst_index": dst, "weight": [hx(x) for x in w]}
         out["regrid_matrices"] = mats
-    out["registry_after_setup"] = [{k: v for k, v in r.items() if k != "values"} for r in R.registry()]
+    out["registry_after_setup"] = R.registry()      # values: 'nan' = never written (uninitialised memory in the reference)
+    out["methods"] = {k: {str(i): m for (mod, i), m in v.items() if mod == 1} for k, v in nml.items() if k.startswith("which_")}
     try:
         R.time_loop(sd["steps"], sd["timestep"])
     except TypeError as e:      # a disassociated pointer is dereferenced: undefined behaviour in the reference

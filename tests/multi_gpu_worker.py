@@ -27,7 +27,7 @@ def main():
     dist.init_process_group(backend="gloo", rank=rank, world_size=world)
     import components.flux_calculator_b200 as m
     from components.flux_calculator_b200 import DeviceArray
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
 
     off, size = m.shard_range(args.cells, rank, world, 512)
     sc = Scenario(args.fset, n=(size, size, size), S=args.S, bias=True, averaging=True, offset=(off, off, off))

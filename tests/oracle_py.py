@@ -56,6 +56,7 @@ class Oracle:
         self.grid_size = tuple(int(x) for x in grid_size)
         self._keep = []
         self._bound = {}
+        self._alloc = {}      # explicit %allocated flags (set_allocated)
 
     def __del__(self):
         try:
@@ -75,10 +76,20 @@ class Oracle:
         self.lib.orc_bind(self.s, surface_type, grid, idx, array.ctypes.data, 1)
         self._fix_allocated()
 
+    def set_allocated(self, surface_type, grid, var, allocated):
+        idx = IDX[var] if isinstance(var, str) else var
+        if allocated is None:
+            self._alloc.pop((surface_type, grid, idx), None)
+        else:
+            self._alloc[(surface_type, grid, idx)] = int(bool(allocated))
+        self._fix_allocated()
+
     def _fix_allocated(self):
         for (i, g, idx), a in self._bound.items():
             own = 1
-            if i == 0:
+            if (i, g, idx) in self._alloc:
+                own = self._alloc[(i, g, idx)]
+            elif i == 0:
                 for (ii, gg, vv), b in self._bound.items():
                     if ii >= 1 and b is a:
                         own = 0
@@ -112,6 +123,24 @@ class Oracle:
     def distribute_shortwave_radiation_flux(self): self.lib.orc_distribute_shortwave_radiation_flux(self.s)
     def average_across_surface_types(self, g, var):
         self.lib.orc_average_across_surface_types(self.s, g, IDX[var] if isinstance(var, str) else var)
+
+    # direction: 0 = u->t, 1 = v->t, 2 = t->u, 3 = t->v (same numbering as fc_set_regrid_matrix)
+    def set_regrid_matrix(self, direction, src_index, dst_index, weight):
+        s = np.ascontiguousarray(src_index, dtype=np.int32)
+        d = np.ascontiguousarray(dst_index, dtype=np.int32)
+        w = np.ascontiguousarray(weight, dtype=np.float64)
+        if not hasattr(self, "_mat"):
+            self._mat = {}
+        self._mat[direction] = (s, d, w)
+
+    def regrid(self, direction, dst, src):
+        class M(C.Structure):
+            _fields_ = [("num_elements", C.c_int64), ("src_index", C.c_void_p), ("dst_index", C.c_void_p), ("weight", C.c_void_p)]
+        s, d, w = self._mat[direction]
+        m = M(s.size, s.ctypes.data, d.ctypes.data, w.ctypes.data)
+        self.lib.orc_regrid.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        self.lib.orc_regrid.restype = None
+        self.lib.orc_regrid(dst.ctypes.data, dst.size, src.ctypes.data, C.byref(m))
 
     def step_early(self, t=0):
         self.set_time(t)

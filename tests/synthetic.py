@@ -3,12 +3,14 @@
 Counter-based RNG keyed by (seed, field name, surface type, grid, GLOBAL cell index): a shard
 [offset, offset+n) of a larger grid sees exactly the values the unsharded grid has at those cells, so
 results can be compared across GPU counts.  Host-side data generation only -- no flux arithmetic.
+
+Test / benchmark infrastructure: lives beside the tests, imports nothing of the product (the CPU arm of bench.py uses
+it without mapping libfluxcalc_b200.so).
 """
 import zlib
 
 import numpy as np
 
-from .fields import IDX, EARLY_OUTPUTS
 
 SEED = 0x5EEDF1C5
 _M64 = np.uint64(0xFFFFFFFFFFFFFFFF)

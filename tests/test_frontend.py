@@ -134,7 +134,7 @@ def test_namelist_and_corrections_drive_a_step(fcmod, nml, tmp_path):
     """flux_calculator.nml + corrections/*.nc -> context -> fused step == oracle configured by hand (MOM5 set, S = 2,
     month from init_date 19611231 + one day = January); a shard (grid_offset) reads its own slice; a month without file
     stays zero with a warning; the reference's start-index quirk (App. F-8) is reproduced on request"""
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     from oracle_py import Oracle
     from tolerances import check_scenario
     n_glob, off, n = 5000, 1024, 3000

@@ -32,7 +32,7 @@ ROUTINES = {
 
 
 def fields(n, seed=1):
-    from components.flux_calculator_b200.synthetic import make_field
+    from synthetic import make_field
     f = {}
     f["TSUR"] = make_field("TSUR", n, seed=seed)
     f["PSUR"] = make_field("PSUR", n, seed=seed)
@@ -160,7 +160,7 @@ def test_properties(fcmod):
 
 def test_unfused_calculators_match_oracle_pass_by_pass(fcmod):
     """the nine calc_* entry points, called one by one like the reference's time loop"""
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     sc = Scenario("MOM5", n=(3001, 2999, 3003), S=2, bias=True, averaging=True)
     o_in, o_out = sc.clone()
     orc = Oracle(sc.n, sc.S)
@@ -187,7 +187,7 @@ def test_unfused_calculators_match_oracle_pass_by_pass(fcmod):
 def test_copy_and_zero_methods_follow_reference_aliasing(fcmod):
     """'copy' aliases surface type 1's array (prepare.F90:36-38); the bias is then added once per surface type to
     the SAME array (calculate.F90:112-116) -- the generic path reproduces it, the fused path declines"""
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     sc = Scenario("CCLM", n=(2001, 2001, 2001), S=3, bias=True, averaging=True)
     sc.methods[("which_flux_mass_evap", 2)] = "copy"
     sc.methods[("which_flux_heat_sensible", 3)] = "zero"

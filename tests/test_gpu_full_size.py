@@ -14,7 +14,7 @@ N = 10_000_000
 @pytest.fixture(scope="module")
 def full(fcmod):
     from components.flux_calculator_b200 import DeviceArray
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     sc = Scenario("CCLM", n=(N, N, N), S=1, bias=True)
     g_in, g_out = sc.clone()
     fc = fcmod.FluxCalculator(sc.n, sc.S)
@@ -35,7 +35,7 @@ def full(fcmod):
 
 
 def test_sampled_cells_match_the_oracle(full):
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     fc, sc, g_in, g_out = full
     idx = np.unique(np.concatenate([np.arange(4096), np.arange(N - 4096, N), np.arange(0, N, 997),
                                     np.arange(511, N, 512 * 296)]))      # tile edges of the persistent schedule included
@@ -81,7 +81,7 @@ def test_two_halves_equal_the_whole(fcmod, full):
     """shard invariance at full size: the second half of the grid computed as its own context (what rank 1 of 2 does)
     gives the bits of the whole-grid run"""
     from components.flux_calculator_b200 import DeviceArray
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     _, sc, g_in, g_out = full
     off, size = fcmod.shard_range(N, 1, 2, 512)
     half = Scenario("CCLM", n=(size,) * 3, S=1, bias=True, offset=(off,) * 3)
@@ -99,3 +99,44 @@ def test_two_halves_equal_the_whole(fcmod, full):
     fc.close()
     for w in wrapped.values():
         w.free()
+
+
+def test_two_surface_types_full_size(fcmod):
+    """BASELINE.json configs[4] at its full size: 10^7 cells per grid, open water + ice with area-fraction averaging, bias;
+    1000 consecutive device-resident steps through fc_run_steps.  Oracle on sampled cells (tile edges of the schedule
+    included), exact averaging identity over all cells."""
+    from components.flux_calculator_b200 import DeviceArray
+    from synthetic import Scenario
+    sc = Scenario("CCLM", n=(N, N, N), S=2, bias=True, averaging=True)
+    g_in, g_out = sc.clone()
+    fc = fcmod.FluxCalculator(sc.n, sc.S)
+    wrapped = sc.apply(fc, g_in, g_out, wrap=lambda a: DeviceArray.from_numpy(a))
+    fc.prepare()
+    assert fc.info("spec_kernel") == 1
+    nsteps, dt = 1000, 600
+    fc.run_steps(0, dt, nsteps)
+    fc.synchronize()
+    for k, a in g_out.items():
+        wrapped[id(a)].download(a)
+    fc.close()
+    for w in wrapped.values():
+        w.free()
+    idx = np.unique(np.concatenate([np.arange(4096), np.arange(N - 4096, N), np.arange(0, N, 1999), np.arange(511, N, 512 * 148)]))
+    small = Scenario("CCLM", n=(idx.size,) * 3, S=2, bias=True, averaging=True)
+    o_in, o_out = small.clone()
+    done = set()
+    for key, a in o_in.items():
+        if id(a) not in done:
+            a[:] = g_in[key][idx]
+            done.add(id(a))
+    small.corrections = np.ascontiguousarray(sc.corrections[idx])
+    orc = Oracle(small.n, small.S)
+    small.apply(orc, o_in, o_out)
+    orc.step_all((nsteps - 1) * dt)
+    small.inputs = o_in
+    check_scenario(small, {k: g_out[k][idx] for k in o_out}, o_out)
+    for (i, g, name) in sc.send:      # average_across_surface_types (calculate.F90:368-385) is exact arithmetic on the per-type values
+        acc = np.zeros(N)
+        for t in (1, 2):
+            acc = acc + g_out[(t, g, name)] * g_in[(t, g, "FARE")]
+        assert np.array_equal(acc, g_out[(0, g, name)]), name

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_synthetic_fields_are_shard_invariant():
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     full = Scenario("CCLM", n=(4096, 4096, 4096), S=2, bias=True, averaging=True)
     part = Scenario("CCLM", n=(1024, 1024, 1024), S=2, bias=True, averaging=True, offset=(2048, 2048, 2048))
     for k, a in part.inputs.items():
@@ -22,7 +22,7 @@ def test_synthetic_fields_are_shard_invariant():
 
 
 def test_scenario_aliasing_mirrors_distribute_input_field():
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     sc = Scenario("CCLM", n=(64, 64, 64), S=3)
     for g in (1, 2, 3):
         assert sc.inputs[(0, g, "PSUR")] is sc.inputs[(1, g, "PSUR")] is sc.inputs[(3, g, "PSUR")]   # basic.F90:349
@@ -33,7 +33,7 @@ def test_scenario_aliasing_mirrors_distribute_input_field():
 
 def test_oracle_ranks_equal_single_rank():
     """P independent ranks over contiguous ranges == one rank (the reference's only parallelism)"""
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     from oracle_py import Oracle
     sc = Scenario("MOM5", n=(5001, 4999, 5003), S=2, bias=True, averaging=True)
     res = []
@@ -61,7 +61,7 @@ def _rank_main(rank, world, port, n_total, q):
     import torch
     import torch.distributed as dist
     import components.flux_calculator_b200 as m
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     from oracle_py import Oracle
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -90,7 +90,7 @@ def _rank_main(rank, world, port, n_total, q):
 
 def test_two_rank_gloo_shards_reproduce_the_unsharded_grid():
     import torch.multiprocessing as mp
-    from components.flux_calculator_b200.synthetic import Scenario
+    from synthetic import Scenario
     from oracle_py import Oracle
     n_total, world = 20_000, 2
     ctx = mp.get_context("spawn")

@@ -47,7 +47,7 @@ class Scales:
     """per-cell magnitudes C of the cancelling terms for every output of one scenario.
 
     inputs: {(type, grid, var): array}; outputs_ref: {(type, grid, var): reference array}; methods: {(which, type): str}
-    (components/flux_calculator_b200/synthetic.Scenario.methods / the golden files' method tables)."""
+    (tests/synthetic.Scenario.methods / the golden files' method tables)."""
 
     def __init__(self, inputs, outputs_ref, methods, num_surface_types):
         self.i, self.o, self.m, self.S = inputs, outputs_ref, methods, num_surface_types
@@ -70,6 +70,9 @@ class Scales:
                     tot = tot + np.abs(self.i[(t, g, "FARE")]) * (np.abs(self.o[(t, g, name)]) + self.of((t, g, name)))
             return tot
         f = lambda v: self.i[(i, g, v)]      # noqa: E731
+        which = {"MEVA": "which_flux_mass_evap", "HLAT": "which_flux_heat_latent", "HSEN": "which_flux_heat_sensible"}.get(name)
+        if which and self.method(which, i) == "copy" and i != 1:      # a pointer alias of surface type 1's array (prepare.F90:36-38)
+            return self.of((1, g, name))
         if name == "MEVA":
             m = self.method("which_flux_mass_evap", i)
             qa = f("QATM")
