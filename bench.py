@@ -36,7 +36,9 @@ WORKLOADS = {
     "C2": ("MOM5", 20_000, 1, True, False, False, "Baltic stand-in 20k cells/grid, MOM5 coefficients + monthly evaporation bias"),
     "C3": ("RCO", 1_000_000, 1, False, False, False, "RCO (Meier 1999) formula set, 1e6 cells/grid"),
     "C4": ("CCLM", 10_000_000, 1, True, False, True, "1e7 cells/grid, CCLM set, all fluxes fused + bias + diagnostics (NCCL all-reduce for N>1)"),
-    "C5": ("CCLM", 10_000_000, 2, True, True, False, "1e7 cells/grid, CCLM set, open water + ice (S=2) with area-fraction averaging, device resident"),
+    "C5": ("CCLM", 10_000_000, 2, True, True, False, "1e7 cells/grid, CCLM set, open water + ice (S=2) with area-fraction averaging, 1000 consecutive steps device resident (fc_run_steps)"),
+    # not a BASELINE.json configuration: the generic fused kernel (more than two surface types)
+    "S3": ("CCLM", 10_000_000, 3, True, True, False, "1e7 cells/grid, CCLM set, three surface types with area-fraction averaging: the generic fused kernel"),
 }
 METRIC = "flux cell-updates/s per coupling step; achieved HBM GB/s vs B200 peak"
 UNIT = "cell-updates/s"

@@ -350,6 +350,7 @@ extern "C" int fc_destroy(fc_context *c)
     cudaFree(c->diag_partials);
     cudaFree(c->diag_chunk_out);
     cudaFree(c->tile_ctr);
+    cudaFree(c->chain_done);
     for (auto &g : c->step_graph)
         if (g) cudaGraphExecDestroy(g);
     p2p_destroy(c);
@@ -555,7 +556,7 @@ extern "C" int fc_set_corrections(fc_context *c, int which, const double *corr, 
     if (!enabled) return FC_OK;
     if (!corr || n != c->n[1]) return fail(c, FC_ERR_ARG, "fc_set_corrections: need corrections(1,12,%lld)", (long long)c->n[1]);
     if (fc_current_month(init_date, 0) == 0) return fail(c, FC_ERR_ARG, "fc_set_corrections: init_date %d is not YYYYMMDD", init_date);
-    if (!c->corr_dev) CUDA_TRY(c, cudaMalloc(&c->corr_dev, (size_t)std::max<int64_t>(n, 1) * 12 * sizeof(double)));
+    if (!c->corr_dev) CUDA_TRY(c, cudaMalloc(&c->corr_dev, (size_t)std::max<int64_t>(corr_stride(n), 2) * 12 * sizeof(double)));
     if (n > 0) {
         bool is_dev, is_pin;
         classify_pointer(corr, &is_dev, &is_pin, nullptr);
@@ -569,7 +570,7 @@ extern "C" int fc_set_corrections(fc_context *c, int which, const double *corr, 
             CUDA_TRY(c, cudaMemcpyAsync(tmp.p, corr, (size_t)n * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
             src = tmp.p;
         }
-        if (launch_transpose_corrections(src, c->corr_dev, n, c->stream)) return fail(c, FC_ERR_CUDA, "transpose_corrections launch failed");
+        if (launch_transpose_corrections(src, c->corr_dev, n, corr_stride(n), c->stream)) return fail(c, FC_ERR_CUDA, "transpose_corrections launch failed");
         c->launches++;
         c->tail_own_step = false;
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -626,6 +627,7 @@ extern "C" int fc_set_option(fc_context *c, const char *name, int64_t value)
     else if (!strcmp(name, "staged")) c->use_staged = (int)std::max<int64_t>(0, std::min<int64_t>(value, 2));
     else if (!strcmp(name, "early_loads")) c->early_loads = value != 0;
     else if (!strcmp(name, "graphs")) c->use_graphs = value != 0;
+    else if (!strcmp(name, "chain")) c->chain_steps = value != 0;
     else if (!strcmp(name, "download")) c->download_sent_only = value != 0;
     else if (!strcmp(name, "dyn_min_tiles")) c->dyn_min_tiles = (int)std::max<int64_t>(0, std::min<int64_t>(value, 1 << 30));
     else if (!strcmp(name, "stream_touched")) {      // the caller enqueued own work on fc_get_stream(): no shortcut across it
@@ -988,7 +990,7 @@ int gen_normal(Gen &G)
 static const double *bias_slab(fc_context *c)
 {
     const int month = fc_current_month(c->init_date, c->time);   // calculate.F90:66-73
-    return c->corr_dev + (size_t)(month - 1) * (size_t)c->n[1];
+    return c->corr_dev + (size_t)(month - 1) * (size_t)corr_stride(c->n[1]);
 }
 
 static int run_ops(fc_context *c, const std::vector<HOp> &ops)
@@ -1322,6 +1324,7 @@ static int prepare_impl(fc_context *c, int strict)
     cudaSetDevice(c->device);
     if (int rc = flush_fold(c)) return rc;
     c->tail_own_step = false;
+    c->chain_key = nullptr;
     c->strict = strict != 0;
     // validation == generating the full pass sequence once (reports what is lacking)
     {
@@ -1589,11 +1592,12 @@ static int attach_tile_counter(fc_context *c, FusedPlan &Q, int slot, unsigned i
 // geometry facts of a bundle's plan that do not change from step to step (cached: each costs a plan build)
 static void bundle_geometry(FusedBundle &F, const FusedPlan &P)
 {
-    if (F.geom_cached) return;
+    const int key = 1 + (int)(reinterpret_cast<uintptr_t>(P.t.bias) & 15u);      // (the bias slab is the only pointer that moves between steps)
+    if (F.geom_cached == key) return;
     F.spec = fused_uses_spec(P) != 0;
     F.claims = F.spec ? fused_dyn_claims(P) : 0u;
     F.fills = F.spec && fused_fills_device(P) != 0;
-    F.geom_cached = true;
+    F.geom_cached = key;
 }
 
 // one device-resident step on the context's stream.  gstep < 0: an ordinary step.  gstep >= 0: step number gstep of a
@@ -1634,6 +1638,21 @@ static int launch_resident(fc_context *c, FusedBundle &F, FusedPlan &P, int gste
         P.tile_base = graph ? (unsigned int)(gstep >> 1) * claims : c->tile_base[tslot];
     }
     if (claims && !F.fills) P.early_loads = 0;
+    // static schedule: record per-CTA completion, and hand over per CTA if the previous launch of the stream was this plan
+    P.chain = 0;
+    P.chain_done = nullptr;
+    if (spec && !claims && !graph) {
+        if (!c->chain_done) {
+            const size_t nb = sizeof(unsigned int) * (size_t)std::max(spec_capacity(1), spec_capacity(2));
+            CUDA_TRY(c, cudaMalloc(&c->chain_done, nb));
+            CUDA_TRY(c, cudaMemsetAsync(c->chain_done, 0, nb, c->stream));
+            c->tail_own_step = false;
+        }
+        P.chain_done = c->chain_done;
+        P.chain_seq = ++c->chain_seq;
+        P.chain = (c->chain_steps && c->early_loads && c->tail_own_step && c->chain_key == (const void *)&F && F.fills) ? 1 : 0;
+        if (!P.chain && !c->tail_own_step) P.early_loads = 0;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (!graph && c->profile_kernel && c->prof_used < 8192 && (c->prof_seq++ % c->profile_kernel) == 0) {
         while (c->prof_ev.size() < c->prof_used + 2) {
@@ -1653,6 +1672,7 @@ static int launch_resident(fc_context *c, FusedBundle &F, FusedPlan &P, int gste
         c->tile_base[tslot] += claims;
         c->fold_pending = false;      // (the launch took the previous step's rows along)
         c->tail_own_step = spec;
+        c->chain_key = (spec && !claims) ? (const void *)&F : nullptr;
     }
     if (P.diag) {
         if (spec) {
@@ -1862,7 +1882,7 @@ constexpr int kGraphSteps = 32;      // step launches per graph (even: the tile 
 int capture_steps(fc_context *c, FusedBundle &F, int month, int nsteps, cudaGraphExec_t *exec)
 {
     FusedPlan P0 = F.plan;
-    if (P0.t.bias) P0.t.bias = c->corr_dev + (size_t)(month - 1) * (size_t)c->n[1];
+    if (P0.t.bias) P0.t.bias = c->corr_dev + (size_t)(month - 1) * (size_t)corr_stride(c->n[1]);
     // everything that allocates or synchronises happens before the capture
     if (int rc = flush_fold(c)) return rc;
     bundle_geometry(F, P0);
@@ -1927,6 +1947,7 @@ extern "C" int fc_run_steps(fc_context *c, int64_t t0, int64_t dt, int nsteps)
             c->time = t0 + (int64_t)(k - 1) * dt;
             if (F.claims) c->tile_base[kMaxChunks] = c->tile_base[kMaxChunks + 1] = (unsigned int)(kGraphSteps / 2) * F.claims;
             c->tail_own_step = F.spec && F.extra.empty();
+            c->chain_key = nullptr;
             if (F.plan.diag) {
                 FusedPlan P = F.plan;
                 P.diag_partials = c->diag_partials;

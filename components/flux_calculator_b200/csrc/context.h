@@ -57,7 +57,8 @@ enum Quantity { Q_QSUR_T = 0, Q_QSUR_U, Q_QSUR_V, Q_MEVA, Q_HLAT, Q_HSEN, Q_MOM,
 
 struct FusedBundle {
     bool ok = false;
-    bool geom_cached = false, spec = false, fills = false;   // step-invariant facts of the plan's geometry (context.cu: bundle_geometry)
+    int geom_cached = 0;      // 0: not yet; else 1 + alignment of the bias slab the facts below were computed for
+    bool spec = false, fills = false;   // step-invariant facts of the plan's geometry (context.cu: bundle_geometry)
     unsigned int claims = 0;
     FusedPlan plan;
     std::vector<int> in_bufs, out_bufs;   // buffers to upload / download in host-pointer mode
@@ -172,6 +173,12 @@ struct fc_context {
     unsigned int *tile_ctr = nullptr;
     unsigned int tile_base[fc::kMaxChunks + 2] = {};
     int tile_par = 0;
+    // chained static steps (spec_kernel.cu): per-CTA completion records, the running launch number, and which bundle issued the
+    // last recorded launch (a step chains to its predecessor only if that was the same plan, directly before it on the stream)
+    unsigned int *chain_done = nullptr;
+    unsigned int chain_seq = 0;
+    const void *chain_key = nullptr;
+    bool chain_steps = true;                // option "chain"
     double *diag_chunk_out = nullptr;       // [kMaxChunks][sum|min|max][kDiagSlots]: per-chunk results (host-pointer pipeline)
     size_t diag_chunk_stride = 0;           // doubles of partial rows + reduce scratch per chunk
     int64_t diag_rows_1 = 0;                // row stride of the device-resident (one launch per step) layout

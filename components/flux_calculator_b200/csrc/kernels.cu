@@ -676,7 +676,8 @@ __global__ void __launch_bounds__(256) oplist_kernel(const __grid_constant__ OpL
 }
 
 // corrections(1,12,n) Fortran order (month fastest) -> [12][n] month-major (bias_corrections.F90:29-30,191)
-__global__ void transpose_corrections_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n)
+// corrections(1,12,n) (month fastest) -> [12][stride] (stride >= n: every month slab starts 16-byte aligned)
+__global__ void transpose_corrections_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t n, int64_t stride)
 {
     __shared__ double tile[12][65];
     const int64_t j0 = (int64_t)blockIdx.x * 64;
@@ -687,7 +688,7 @@ __global__ void transpose_corrections_kernel(const double *__restrict__ src, dou
     __syncthreads();
     for (int e = threadIdx.x; e < 12 * 64; e += blockDim.x) {
         const int m = e / 64, jj = e % 64;
-        if (j0 + jj < n) dst[(int64_t)m * n + j0 + jj] = tile[m][jj];
+        if (j0 + jj < n) dst[(int64_t)m * stride + j0 + jj] = tile[m][jj];
     }
 }
 
@@ -946,10 +947,10 @@ int launch_oplist(const OpList &ops, const Consts &c, int64_t n, cudaStream_t st
     return (int)cudaGetLastError();
 }
 
-int launch_transpose_corrections(const double *src, double *dst, int64_t n, cudaStream_t stream)
+int launch_transpose_corrections(const double *src, double *dst, int64_t n, int64_t stride, cudaStream_t stream)
 {
     if (n <= 0) return 0;
-    transpose_corrections_kernel<<<(int)((n + 63) / 64), 256, 0, stream>>>(src, dst, n);
+    transpose_corrections_kernel<<<(int)((n + 63) / 64), 256, 0, stream>>>(src, dst, n, stride);
     return (int)cudaGetLastError();
 }
 

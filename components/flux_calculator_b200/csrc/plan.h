@@ -162,7 +162,10 @@ struct FusedPlan {
     int early_loads;         // the previous operation of the stream is this library's own step kernel (which writes no
                              // input): the producers may start their first bulk copies before griddepcontrol.wait
     int dyn_min_tiles;       // dynamic schedule from this many tiles per CTA on (0: the built-in default)
+    int chain;               // static schedule: the previous launch of the stream was this very plan -> its CTA b hands over to this
+    unsigned int chain_seq;  //   launch's CTA b (spec_kernel.cu); number of this launch, and where the CTAs record it
     int pad4;
+    unsigned int *chain_done;
     unsigned int tile_base;  // dynamic tile schedule of the specialised kernel without diagnostics: the counter's value
     unsigned int *tile_counter;   // before this launch (it is never reset, see spec_kernel.cu)
     double *diag_out;        // [sum|min|max][kDiagSlots] result of this step
@@ -207,7 +210,8 @@ int spec_capacity(int num_surface_types);
 int fused_fills_device(const FusedPlan &plan);      // the specialised launch of this plan occupies every CTA slot of the device
 unsigned int fused_dyn_claims(const FusedPlan &plan);      // kernels.cu: the same for a whole fused step (0: static schedule)
 unsigned long long read_spec_exact_calls();
-int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, cudaStream_t stream);
+int launch_transpose_corrections(const double *corr_fortran, double *corr_month_major, int64_t n, int64_t stride, cudaStream_t stream);
+inline int64_t corr_stride(int64_t n) { return (n + 1) & ~int64_t(1); }      // cells between two month slabs: even, so that each slab is 16-byte aligned
 int launch_regrid_csr(const int64_t *row_ptr, const int32_t *src_idx, const double *weight, const double *src,
                       double *dst, int64_t n_dst, cudaStream_t stream);
 

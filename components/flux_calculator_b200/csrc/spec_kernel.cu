@@ -140,6 +140,9 @@ struct SpecPlan {
     DiagFold prev;                    // rows of the previous launch, folded here while the ring fills (nslots == 0: none)
     int early_loads;                  // first bulk copies before griddepcontrol.wait (previous kernel = own step)
     int dyn;                          // this launch uses the dynamic schedule
+    int chain;                        // static schedule: the previous launch of the stream is the same plan -> per-CTA hand-over
+    unsigned int seq;                 // number of this launch in the context's sequence of static launches
+    unsigned int *done;               // [CTA]: seq of the last launch whose CTA of that index has stored everything (null: not recorded)
     int area_ahead;                   // fetch the cell areas one tile ahead (pays while the launch is latency bound: few tiles per CTA)
     unsigned int tile_base;           // dynamic schedule: value of *tile_counter before this launch's first claim
     unsigned int *tile_counter;       // dynamic schedule: tiles are claimed with atomicAdd (never reset: the host tracks the base)
@@ -926,7 +929,7 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int SET, int NS, int DIAG>
+template <int SET, int NS, int DIAG, bool DYN>
 __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<NS>::kMaxRegs) flux_spec_kernel(const __grid_constant__ SpecPlan p)
 {
     using GEO = SpecGeom<NS>;
@@ -938,7 +941,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
     __shared__ uint64_t fullT[kSpecMaxBars], emptyT[kSpecMaxBars], fullU[kSpecMaxBars], emptyU[kSpecMaxBars];
     __shared__ int flagged[GEO::kWarps][kSpecBadCap];
     __shared__ int nflagged[GEO::kWarps];
-    constexpr bool DYN = (DIAG == 0) && FC_SPEC_DYNAMIC;      // instantiations that carry the dynamic schedule (chosen per launch: p.dyn)
+    static_assert(!DYN || DIAG == 0, "the dynamic schedule exists without diagnostics only");
     __shared__ int tileT[DYN ? kSpecMaxBars : 1], tileU[DYN ? kSpecMaxBars : 1];      // dynamic schedule: tile of each barrier slot
     __shared__ WarpSums<NS, DIAG> ws;
     __shared__ double wacc[(NS > 1 && DIAG) ? GEO::kWarps : 1][(NS > 1 && DIAG) ? (DIAG >= 2 ? 3 : 1) * kDiagAccMax : 1];
@@ -971,14 +974,32 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
     // the producer warp when the host vouches that the previous kernel is this library's own step, which writes none
     // of the arrays the producer reads: it fills the ring first and waits afterwards (before it folds that step's rows)
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const bool early_producer = p.early_loads && (threadIdx.x >> 5) == GEO::kWarps;
-    if (!early_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
-    if constexpr (DYN) {      // (its producer never has to wait: it reads input arrays and the tile counter only)
-        if (p.dyn) {
-            spec_dynamic_body<SET, NS>(p, ring, fullT, emptyT, fullU, emptyU, tileT, tileU, flagged, nflagged);
-            return;
+    const bool producer_warp = (threadIdx.x >> 5) == GEO::kWarps;
+    const bool early_producer = p.early_loads && producer_warp;
+    // chained steps (static schedule, same plan as the previous launch of the stream): CTA b writes exactly the cells CTA b
+    // of the previous step wrote, so it only has to wait for THAT CTA, not for the whole grid -- the previous step's slow SMs
+    // no longer hold up the fast ones, the steps flow into each other per SM.  Everything that does need the whole previous
+    // grid (its diagnostics rows) still waits for it, but at the END of this CTA's work, when it has long completed.
+    const bool chain = !DYN && p.chain;
+    if (!early_producer && !chain) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (chain && !producer_warp) {
+        if (threadIdx.x == 0) {
+            const unsigned int want = p.seq - 1u;
+            unsigned int v;
+            // (bounded: the CTA waited for is resident and never waits for this one, so the bound -- about a second --
+            // is never reached; it is there so that a host-side sequencing error cannot turn into a hung device)
+            for (unsigned int spins = 0; spins < (1u << 24); ++spins) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.done + blockIdx.x) : "memory");
+                if ((int)(v - want) >= 0) break;
+                __nanosleep(64);
+            }
         }
+        consumer_barrier<NS>();
     }
+    if constexpr (DYN) {      // (its producer never has to wait: it reads input arrays and the tile counter only)
+        spec_dynamic_body<SET, NS>(p, ring, fullT, emptyT, fullU, emptyU, tileT, tileU, flagged, nflagged);
+        return;
+    } else {
 
     // static schedule: this CTA takes positions b, b+G, b+2G, ... of the tile list [t tiles | u tiles | v tiles]
     const int G = gridDim.x, b = blockIdx.x;
@@ -1014,11 +1035,14 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
                 if (i == nfill) {
                     // the ring is filling: now (a) honour the stream order if the fill ran ahead of it, (b) fold the previous
                     // step's diagnostics rows -- CTA b takes compact slots b, b + G, ... with the whole warp -- and
-                    // (c) retire the lanes that issue nothing
-                    if (early_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
-                    __syncwarp();
-                    for (int cs = b; cs < p.prev.nslots; cs += G) diag_fold_slot(p.prev, cs);
-                    if (!FC_SPEC_PAR_PRODUCER && lane != 0) return;
+                    // (c) retire the lanes that issue nothing.  Chained steps fold at the very end instead (the previous
+                    // grid has to be complete for it), so the lanes of a folding warp stay.
+                    if (!chain) {
+                        if (early_producer) asm volatile("griddepcontrol.wait;" ::: "memory");
+                        __syncwarp();
+                        for (int cs = b; cs < p.prev.nslots; cs += G) diag_fold_slot(p.prev, cs);
+                    }
+                    if (!FC_SPEC_PAR_PRODUCER && lane != 0 && !(chain && b < p.prev.nslots)) return;
                 }
                 if (i >= ring0) break;
                 if (i >= NT) {
@@ -1077,7 +1101,7 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
                     if (FC_SPEC_PAR_PRODUCER) {
                         if (lane < Lay<SET, NS>::NUV && p.src[ph][lane])
                             bulk_g2s(dst + lane * GEO::kSlotBytes, p.src[ph][lane] + cell, GEO::kSlotBytes, &fullU[bi]);
-                    } else {
+                    } else if (lane == 0) {
 #pragma unroll 1
                         for (int a = 0; a < Lay<SET, NS>::NUV; ++a)
                             if (p.src[ph][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[ph][a] + cell, GEO::kSlotBytes, &fullU[bi]);
@@ -1086,6 +1110,11 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
                     if (++bi == LU) bi = 0;
                 }
             }
+        }
+        if (chain && b < p.prev.nslots) {      // chained step: the previous step's rows, now that its grid is certainly complete
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            __syncwarp();
+            for (int cs = b; cs < p.prev.nslots; cs += G) diag_fold_slot(p.prev, cs);
         }
         return;
     }
@@ -1245,7 +1274,17 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
             }
         }
     }
-    if (DIAG) diag_finish<NS, DIAG>(p, ws);
+    // hand-over to the same CTA of the next step: every consumer warp has issued its last store
+    consumer_barrier<NS>();
+    if (threadIdx.x == 0 && p.done) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.done + blockIdx.x), "r"(p.seq) : "memory");
+    }
+    if (DIAG) {
+        if (chain) asm volatile("griddepcontrol.wait;" ::: "memory");      // the rows go where the step before the previous one left its own
+        diag_finish<NS, DIAG>(p, ws);
+    }
+    }      // static schedule
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1442,6 +1481,9 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     sp.tile_counter = p.tile_counter;
     sp.tile_base = p.tile_base;
     sp.dyn = p.dyn_min_tiles;
+    sp.chain = p.chain;
+    sp.seq = p.chain_seq;
+    sp.done = p.chain_done;
     sp.early_loads = p.early_loads;
     *set_out = set;
     return true;
@@ -1491,16 +1533,16 @@ unsigned int spec_dyn_claims(const FusedPlan &p, const int64_t first[3], const i
     return (unsigned int)sp.ntiles[0] + (nuv + kDynUvBatch - 1) / kDynUvBatch + 2u * (unsigned)spec_grid(sp);
 }
 
-template <int SET, int NS, int DIAG>
+template <int SET, int NS, int DIAG, bool DYN>
 static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stream)
 {
     const size_t tb = (size_t)sp.t_stages * sp.t_stage_bytes, ub = (size_t)sp.u_stages * sp.u_stage_bytes;
     const size_t smem = tb > ub ? tb : ub;
     static size_t configured = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(flux_spec_kernel<SET, NS, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(flux_spec_kernel<SET, NS, DIAG, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(flux_spec_kernel<SET, NS, DIAG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(flux_spec_kernel<SET, NS, DIAG, DYN>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured = smem;
     }
@@ -1517,15 +1559,16 @@ static cudaError_t spec_launch_t(const SpecPlan &sp, int grid, cudaStream_t stre
     attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, flux_spec_kernel<SET, NS, DIAG>, sp);
+    return cudaLaunchKernelEx(&cfg, flux_spec_kernel<SET, NS, DIAG, DYN>, sp);
 }
 
 template <int SET, int NS>
 static cudaError_t spec_launch_d(const SpecPlan &sp, int grid, cudaStream_t stream)
 {
-    if (sp.diag >= 2) return spec_launch_t<SET, NS, 2>(sp, grid, stream);
-    if (sp.diag == 1) return spec_launch_t<SET, NS, 1>(sp, grid, stream);
-    return spec_launch_t<SET, NS, 0>(sp, grid, stream);
+    if (sp.diag >= 2) return spec_launch_t<SET, NS, 2, false>(sp, grid, stream);
+    if (sp.diag == 1) return spec_launch_t<SET, NS, 1, false>(sp, grid, stream);
+    if (FC_SPEC_DYNAMIC && sp.dyn) return spec_launch_t<SET, NS, 0, true>(sp, grid, stream);
+    return spec_launch_t<SET, NS, 0, false>(sp, grid, stream);
 }
 
 int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[3], cudaStream_t stream)
@@ -1537,6 +1580,7 @@ int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[
     const int grid = spec_grid(sp);
     sp.dyn = spec_wants_dyn(sp) ? 1 : 0;
     if (sp.dyn && !sp.tile_counter) return (int)cudaErrorInvalidValue;
+    if (sp.dyn) sp.chain = 0;
     // cell areas one tile ahead while there are few tiles per CTA (8-GPU shard of C4, 25 tiles per CTA: 61.3 -> 58.3 us);
     // with many the kernel is DRAM bound and the earlier loads only synchronise the warps (10^7 cells: 0.433 -> 0.455 ms)
     sp.area_ahead = ((int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] < (int64_t)64 * grid) ? 1 : 0;

@@ -459,3 +459,44 @@ def test_static_inputs_and_sent_only_download(fcmod):
     assert np.array_equal(a_out[(1, 1, "MEVA")], b_out[(1, 1, "MEVA")])
     fa.close()
     fb.close()
+
+
+@pytest.mark.parametrize("S,diag", [(1, 0), (1, 1), (2, 1)])
+def test_chained_steps_keep_the_stream_order(fcmod, S, diag):
+    """consecutive device-resident steps of one plan hand over per CTA instead of waiting for the whole previous grid:
+    the results of the LAST step must win in every cell (the bias month alternates from step to step, so a stale store
+    of the step before would show), with and without the option, and the diagnostics are those of the last step"""
+    from components.flux_calculator_b200 import DeviceArray
+    from synthetic import Scenario
+    sc = Scenario("CCLM", n=(512 * 900 + 3, 512 * 900, 512 * 901), S=S, bias=True, averaging=True, init_date=19610101)
+    times = [0 if k % 2 == 0 else 86400 * 45 for k in range(101)]      # January / February alternating; the last one is January
+    res = {}
+    for chain in (1, 0):
+        g_in, g_out = sc.clone()
+        fc = fcmod.FluxCalculator(sc.n, sc.S)
+        wrapped = sc.apply(fc, g_in, g_out, wrap=lambda a: DeviceArray.from_numpy(a))
+        if diag:
+            for g in (1, 2, 3):
+                fc.set_area(g, sc.area[g])
+            fc.set_option("diagnostics", diag)
+        fc.set_option("chain", chain)
+        fc.set_option("dyn_min_tiles", 1 << 30)      # static schedule (the dynamic one never chains)
+        fc.prepare()
+        for t in times:
+            fc.step_all(t)
+        fc.synchronize()
+        for k, a in g_out.items():
+            wrapped[id(a)].download(a)
+        res[chain] = (g_out, {k: fc.diagnostics(*k)[0] for k in g_out} if diag else None)
+        fc.close()
+        for w in wrapped.values():
+            w.free()
+    o_in, o_out = sc.clone()
+    orc = Oracle(sc.n, sc.S)
+    sc.apply(orc, o_in, o_out)
+    orc.step_all(times[-1])
+    compare(sc, o_out, res[1][0])
+    for k in res[1][0]:
+        assert np.array_equal(res[1][0][k], res[0][0][k], equal_nan=True), k
+    if diag:
+        assert res[1][1] == res[0][1]
