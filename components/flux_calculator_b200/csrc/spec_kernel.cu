@@ -121,6 +121,7 @@ struct SpecPlan {
     int64_t first[3];                 // first cell of the range on each grid
     int64_t end[3];                   // one past its last cell
     int ntiles[3];                    // ceil(cells / tile): the last tile of a grid may be partial (guarded path)
+    int rot[3];                       // static schedule: CTA that takes tile 0 of each grid
     int t_stages, u_stages;           // the two carvings of the ring
     int t_stage_bytes, u_stage_bytes;
     int t_bars, u_bars;               // lcm(teams, stages): tile i uses barrier i mod bars (one per (team, stage) pair) in phase i / bars
@@ -1007,15 +1008,15 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
     int cnt0, cnt1, cnt2;
     int64_t tl0, tl1, tl2;      // first tile of this CTA inside each grid
     {
-        auto sched = [&](int64_t off, int64_t n, int &cnt, int64_t &tl) {
-            int64_t x0 = b;
-            if (off > b) x0 = b + ((off - b + G - 1) / G) * G;
-            cnt = (x0 < off + n) ? (int)((off + n - x0 + G - 1) / G) : 0;
-            tl = x0 - off;
+        // grid g's tiles go round the CTAs starting at CTA rot[g]: CTA b takes tiles (b - rot[g]) mod G, + G, + 2G, ...  With
+        // rot = {0, nt, nt + nu} (what the host sets) this is "positions b, b + G, ... of the concatenated list"
+        auto sched = [&](int rot, int64_t n, int &cnt, int64_t &tl) {
+            tl = (b - rot + G) % G;
+            cnt = (tl < n) ? (int)((n - tl + G - 1) / G) : 0;
         };
-        sched(0, p.ntiles[0], cnt0, tl0);
-        sched(p.ntiles[0], p.ntiles[1], cnt1, tl1);
-        sched((int64_t)p.ntiles[0] + p.ntiles[1], p.ntiles[2], cnt2, tl2);
+        sched(p.rot[0], p.ntiles[0], cnt0, tl0);
+        sched(p.rot[1], p.ntiles[1], cnt1, tl1);
+        sched(p.rot[2], p.ntiles[2], cnt2, tl2);
     }
     // the last tile of a grid may be partial: its CTA takes it before the ring tiles, through guarded global accesses
     auto partial = [&](int ph, int cnt, int64_t tl) {
@@ -1581,6 +1582,13 @@ int spec_launch(const FusedPlan &p, const int64_t first[3], const int64_t cells[
     sp.dyn = spec_wants_dyn(sp) ? 1 : 0;
     if (sp.dyn && !sp.tile_counter) return (int)cudaErrorInvalidValue;
     if (sp.dyn) sp.chain = 0;
+    // static schedule: the three grids follow each other round the CTAs (positions b, b + G, ... of the concatenated list).
+    // (Choosing the starts so that the CTAs with one tile more spread evenly over the SMs by bytes was tried for the chained
+    // 8-GPU shards -- 2480 vs 2404 KB per SM with plain succession -- and measured no gain: 61.2 vs 60.2 us, within the
+    // box-to-box spread; profiles/README.md.)
+    sp.rot[0] = 0;
+    sp.rot[1] = grid > 0 ? sp.ntiles[0] % grid : 0;
+    sp.rot[2] = grid > 0 ? (int)(((int64_t)sp.ntiles[0] + sp.ntiles[1]) % grid) : 0;
     // cell areas one tile ahead while there are few tiles per CTA (8-GPU shard of C4, 25 tiles per CTA: 61.3 -> 58.3 us);
     // with many the kernel is DRAM bound and the earlier loads only synchronise the warps (10^7 cells: 0.433 -> 0.455 ms)
     sp.area_ahead = ((int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] < (int64_t)64 * grid) ? 1 : 0;
