@@ -8,10 +8,8 @@
 #include <cstdio>
 #include <cstring>
 #include <cctype>
-#include <mutex>
 #include <sched.h>
 #include <set>
-#include <unordered_map>
 
 using namespace fc;
 
@@ -187,66 +185,17 @@ extern "C" int fc_shard_range(int64_t n, int rank, int nranks, int64_t align, in
     return FC_OK;
 }
 
-// Device arrays handed out by the library start at STAGGERED offsets inside their allocation (option env
-// FC_ALLOC_STAGGER = bytes, a multiple of 256; the k-th allocation is shifted by (k mod 32) * stagger): equally sized
-// arrays allocated back to back would otherwise all sit at the same offset of their 2 MB pages, and the 20-30 streams
-// a tile reads and writes in lock step would walk the DRAM channels in phase.
-namespace {
-std::mutex g_alloc_mu;
-std::unordered_map<void *, void *> g_alloc_base;      // returned pointer -> cudaMalloc pointer
-int64_t alloc_stagger()
-{
-    static const int64_t v = [] {
-        const char *e = getenv("FC_ALLOC_STAGGER");
-        int64_t x = e ? atoll(e) : 0;
-        return x < 0 ? 0 : (x & ~int64_t(255));
-    }();
-    return v;
-}
-unsigned g_alloc_count = 0;
-}  // namespace
-
-namespace fc {
-cudaError_t staggered_malloc(void **dptr, size_t nbytes)
-{
-    const int64_t st = alloc_stagger();
-    if (st == 0) return cudaMalloc(dptr, nbytes);
-    void *base = nullptr;
-    const cudaError_t e = cudaMalloc(&base, nbytes + (size_t)st * 32);
-    if (e != cudaSuccess) return e;
-    std::lock_guard<std::mutex> lk(g_alloc_mu);
-    void *p = (char *)base + (size_t)st * (g_alloc_count++ % 32u);
-    g_alloc_base[p] = base;
-    *dptr = p;
-    return cudaSuccess;
-}
-cudaError_t staggered_free(void *dptr)
-{
-    if (!dptr) return cudaSuccess;
-    void *base = dptr;
-    {
-        std::lock_guard<std::mutex> lk(g_alloc_mu);
-        auto it = g_alloc_base.find(dptr);
-        if (it != g_alloc_base.end()) {
-            base = it->second;
-            g_alloc_base.erase(it);
-        }
-    }
-    return cudaFree(base);
-}
-}  // namespace fc
-
 extern "C" int fc_device_malloc(int device, int64_t nbytes, void **dptr)
 {
     if (!dptr || nbytes < 0) return fail(nullptr, FC_ERR_ARG, "fc_device_malloc: bad argument");
     CUDA_TRY(nullptr, cudaSetDevice(device));
-    CUDA_TRY(nullptr, staggered_malloc(dptr, (size_t)std::max<int64_t>(nbytes, 8)));
+    CUDA_TRY(nullptr, cudaMalloc(dptr, (size_t)std::max<int64_t>(nbytes, 8)));
     return FC_OK;
 }
 extern "C" int fc_device_free(int device, void *dptr)
 {
     CUDA_TRY(nullptr, cudaSetDevice(device));
-    CUDA_TRY(nullptr, staggered_free(dptr));
+    CUDA_TRY(nullptr, cudaFree(dptr));
     return FC_OK;
 }
 extern "C" int fc_host_malloc_pinned(int64_t nbytes, void **hptr)
@@ -342,7 +291,7 @@ extern "C" int fc_destroy(fc_context *c)
     nccl_destroy(c);
     for (auto &b : c->bufs) {
         if (b.registered) cudaHostUnregister(b.user);
-        if (!b.user_is_device && b.dev) staggered_free(b.dev);
+        if (!b.user_is_device && b.dev) cudaFree(b.dev);
     }
     cudaFree(c->corr_dev);
     for (int g = 1; g <= 3; ++g)
@@ -383,7 +332,7 @@ static void release_buffer(fc_context *c, int b)
     Buffer &B = c->bufs[b];
     if (--B.refs > 0) return;
     if (B.registered) cudaHostUnregister(B.user);
-    if (!B.user_is_device && B.dev) staggered_free(B.dev);
+    if (!B.user_is_device && B.dev) cudaFree(B.dev);
     B = Buffer();   // tombstone (indices of other buffers stay valid)
 }
 
@@ -421,7 +370,7 @@ extern "C" int fc_bind_field(fc_context *c, int i, int g, int idx, double *p, in
     if (B.user_is_device) {
         B.dev = p;
     } else {
-        CUDA_TRY(c, staggered_malloc((void **)&B.dev, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
+        CUDA_TRY(c, cudaMalloc(&B.dev, (size_t)std::max<int64_t>(n, 1) * sizeof(double)));
         if (c->pin_host && !B.user_is_pinned && n > 0) {
             if (cudaHostRegister(p, (size_t)n * sizeof(double), cudaHostRegisterPortable) == cudaSuccess) B.registered = true;
             else cudaGetLastError();

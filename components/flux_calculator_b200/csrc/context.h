@@ -107,8 +107,6 @@ int fail(fc_context *ctx, int code, const char *fmt, ...);
 int classify_pointer(const void *p, bool *is_device, bool *is_pinned, int *device);
 int diag_fetch(fc_context *c);
 int flush_fold(fc_context *c);
-cudaError_t staggered_malloc(void **dptr, size_t nbytes);
-cudaError_t staggered_free(void *dptr);
 
 }  // namespace fc
 
