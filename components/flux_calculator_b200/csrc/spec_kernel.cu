@@ -63,6 +63,12 @@ constexpr int kSpecV = 2;
 #define FC_SPEC1_REGS 96            // one type: 2 CTAs x 9 warps per SM (112 would still fit the register file on paper, but measured
                                     // 0.57 ms instead of 0.43 ms on C4: the second CTA no longer becomes resident)
 #endif
+#ifndef FC_SPEC_BYPASS
+#define FC_SPEC_BYPASS 0            // bit (NS - 1) set: in the kernels for NS surface types the two t-grid arrays that are used exactly once per surface
+#endif                              // type and feed no transcendental -- RSDD (copied through) and the evaporation bias (added) -- do NOT travel through
+                                    // the ring: each consumer thread fetches its own 16 bytes of them straight from global memory before it waits for
+                                    // the tile.  Two types: the t stage shrinks from 15 to 13 arrays (60 -> 52 KB), which buys a FOURTH stage (two in
+                                    // work, two in flight instead of one); one type: 11 -> 9 arrays, three stages per CTA instead of two.
 #ifndef FC_SPEC_PAR_PRODUCER
 #define FC_SPEC_PAR_PRODUCER 0      // 0: lane 0 of the producer warp issues all bulk copies of a tile; 1: lane a issues slot a
 #endif
@@ -80,6 +86,8 @@ struct SpecGeom {
     // registers per thread, stated directly (see the two macros above)
     static constexpr int kMaxRegs = (NS == 1) ? FC_SPEC1_REGS : FC_SPEC2_REGS;
 };
+template <int NS>
+constexpr bool kSpecBypass = ((FC_SPEC_BYPASS >> (NS - 1)) & 1) != 0;
 constexpr int kSpecMaxStages = 16;
 constexpr int kSpecMaxBars = 32;                         // barriers per set: lcm(teams, stages) <= 2 * 16
 constexpr int kSpecMaxSlots = 16;
@@ -97,15 +105,18 @@ enum SpecSet { SET_BULK = 0, SET_RCO = 1 };
 template <int SET, int NS>
 struct Lay {
     static constexpr int kPer = (NS == 1) ? 2 : 3;       // per-type arrays: FICE, TSUR (, FARE)
-    // t grid
-    static constexpr int PSUR = 0, QATM = 1, TATM = 2, UATM = 3, VATM = 4, RSDD = 5, BIAS = 6;
-    static constexpr int AEV = 7, PATM = 8;              // bulk only
-    static constexpr int kShared = (SET == SET_BULK) ? 9 : 7;
+    // t grid.  With FC_SPEC_BYPASS for this NS, RSDD and BIAS move behind the staged slots (they do not travel through the ring)
+    static constexpr bool kBy = kSpecBypass<NS>;
+    static constexpr int PSUR = 0, QATM = 1, TATM = 2, UATM = 3, VATM = 4;
+    static constexpr int AEV = kBy ? 5 : 7, PATM = kBy ? 6 : 8;      // bulk only
+    static constexpr int kShared = (SET == SET_BULK ? 7 : 5) + (kBy ? 0 : 2);
     __host__ __device__ static constexpr int FICE(int i) { return kShared + kPer * i; }
     __host__ __device__ static constexpr int TSUR(int i) { return kShared + kPer * i + 1; }
     __host__ __device__ static constexpr int FARE(int i) { return kShared + kPer * i + 2; }
     static constexpr int ASE = kShared + kPer * NS;      // bulk/MOM5 only (CHEA != CMOI)
-    static constexpr int NT = ASE + (SET == SET_BULK ? 1 : 0);
+    static constexpr int kStagedT = ASE + (SET == SET_BULK ? 1 : 0);      // t slots [0, kStagedT) travel through the ring
+    static constexpr int RSDD = kBy ? kStagedT : 5, BIAS = kBy ? kStagedT + 1 : 6;
+    static constexpr int NT = kStagedT + (kBy ? 2 : 0);
     // u / v grid
     static constexpr int U_UATM = 0, U_VATM = 1, U_PSUR = 2, U_AMOM = 3;
     static constexpr int kUShared = (SET == SET_BULK) ? 4 : 2;
@@ -122,6 +133,7 @@ struct SpecPlan {
     int64_t end[3];                   // one past its last cell
     int ntiles[3];                    // ceil(cells / tile): the last tile of a grid may be partial (guarded path)
     int rot[3];                       // static schedule: CTA that takes tile 0 of each grid
+    int t_staged;                     // t slots [0, t_staged) travel through the ring (FC_SPEC_BYPASS: the last two do not)
     int t_stages, u_stages;           // the two carvings of the ring
     int t_stage_bytes, u_stage_bytes;
     int t_bars, u_bars;               // lcm(teams, stages): tile i uses barrier i mod bars (one per (team, stage) pair) in phase i / bars
@@ -208,6 +220,22 @@ struct LdStage {
     const char *base;
     __device__ __forceinline__ S2 operator()(int slot) const
     {
+        const double2 t = *reinterpret_cast<const double2 *>(base + slot * SLOT_BYTES);
+        S2 r;
+        r.v[0] = t.x;
+        r.v[1] = t.y;
+        return r;
+    }
+};
+// hot path with FC_SPEC_BYPASS: the same, except that RSDD and BIAS come from registers (fetched by spec_fetch_direct)
+template <int SLOT_BYTES, int RSDD, int BIAS>
+struct LdStageDirect {
+    const char *base;
+    S2 rsdd, bias;
+    __device__ __forceinline__ S2 operator()(int slot) const
+    {
+        if (slot == RSDD) return rsdd;
+        if (slot == BIAS) return bias;
         const double2 t = *reinterpret_cast<const double2 *>(base + slot * SLOT_BYTES);
         S2 r;
         r.v[0] = t.x;
@@ -637,6 +665,37 @@ __device__ __forceinline__ void spec_uv_chain(M &m, const SpecPlan &p, int north
     }
 }
 
+// FC_SPEC_BYPASS: this thread's 16 bytes of the two t-grid arrays that do not travel through the ring.  Issued before the
+// thread waits for its tile (static schedule: the cells are known in advance) or right after (dynamic schedule); first
+// used a good way into the chain (the bias after the first QSUR and MEVA, RSDD at the end of the first surface type).
+template <int SET, int NS>
+__device__ __forceinline__ void spec_fetch_direct(const SpecPlan &p, int64_t j, S2 &rsdd, S2 &bias)
+{
+    using L = Lay<SET, NS>;
+    double2 r = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+    if (p.has_rsdr) r = __ldg(reinterpret_cast<const double2 *>(p.src[0][L::RSDD] + j));
+    if (p.has_bias) b = __ldg(reinterpret_cast<const double2 *>(p.src[0][L::BIAS] + j));
+    rsdd.v[0] = r.x;
+    rsdd.v[1] = r.y;
+    bias.v[0] = b.x;
+    bias.v[1] = b.y;
+}
+
+// the t chain of one full tile out of a ring stage
+template <int SET, int NS, class ST, class DG>
+__device__ __forceinline__ void spec_t_tile(FastVec<kSpecV> &m, const SpecPlan &p, const char *base, const S2 &rsdd, const S2 &bias,
+                                            const ST &st, DG &dg)
+{
+    using L = Lay<SET, NS>;
+    if constexpr (kSpecBypass<NS>) {
+        const LdStageDirect<SpecGeom<NS>::kSlotBytes, L::RSDD, L::BIAS> ld{base, rsdd, bias};
+        spec_t_chain<SET, NS>(m, p, ld, st, dg);
+    } else {
+        const LdStage<SpecGeom<NS>::kSlotBytes> ld{base};
+        spec_t_chain<SET, NS>(m, p, ld, st, dg);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // cold epilogue of one phase of one warp: recompute the flagged tiles with the IEEE routines (scalar, from global
 // memory), then rebuild this warp's diagnostics of the phase from the stored outputs in the hot loop's order:
@@ -785,7 +844,7 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
                     mbar_expect_tx(&fullT[bi], p.tx_bytes[0]);
                     char *dst = ring + (size_t)st * p.t_stage_bytes;
 #pragma unroll 1
-                    for (int a = 0; a < L::NT; ++a)
+                    for (int a = 0; a < L::kStagedT; ++a)
                         if (p.src[0][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[0][a] + cell, GEO::kSlotBytes, &fullT[bi]);
                 }
                 next();
@@ -891,10 +950,15 @@ __device__ __forceinline__ void spec_dynamic_body(const SpecPlan &p, char *ring,
             FastVec<kSpecV> m;
             bool bad;
             if (!(id & kDynPartial)) {
-                const LdStage<GEO::kSlotBytes> ld{ring + (size_t)s * sbytes + toff};
                 const StPair st{j};
-                if (uv) spec_uv_chain<SET, NS>(m, p, north, ld, st, nd);
-                else spec_t_chain<SET, NS>(m, p, ld, st, nd);
+                if (uv) {
+                    const LdStage<GEO::kSlotBytes> ld{ring + (size_t)s * sbytes + toff};
+                    spec_uv_chain<SET, NS>(m, p, north, ld, st, nd);
+                } else {
+                    S2 d_rsdd, d_bias;
+                    if constexpr (kSpecBypass<NS>) spec_fetch_direct<SET, NS>(p, j, d_rsdd, d_bias);
+                    spec_t_tile<SET, NS>(m, p, ring + (size_t)s * sbytes + toff, d_rsdd, d_bias, st, nd);
+                }
                 bad = m.bad();
             } else {
                 const int64_t left = p.end[ph] - j;
@@ -1059,11 +1123,11 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
                 char *dst = ring + (size_t)st * p.t_stage_bytes;
                 static_assert(Lay<SET, NS>::NT <= 32 && Lay<SET, NS>::NUV <= 32, "one lane per slot");
                 if (FC_SPEC_PAR_PRODUCER) {
-                    if (lane < Lay<SET, NS>::NT && p.src[0][lane])
+                    if (lane < Lay<SET, NS>::kStagedT && p.src[0][lane])
                         bulk_g2s(dst + lane * GEO::kSlotBytes, p.src[0][lane] + cell, GEO::kSlotBytes, &fullT[bi]);
                 } else if (lane == 0) {
 #pragma unroll 1
-                    for (int a = 0; a < Lay<SET, NS>::NT; ++a)
+                    for (int a = 0; a < Lay<SET, NS>::kStagedT; ++a)
                         if (p.src[0][a]) bulk_g2s(dst + a * GEO::kSlotBytes, p.src[0][a] + cell, GEO::kSlotBytes, &fullT[bi]);
                 }
                 if (++st == NT) st = 0;
@@ -1165,11 +1229,12 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
                 dg.area.v[1] = a_next.y;
                 if (p.area_ahead && i + TEAMS < ring0) a_next = __ldg(reinterpret_cast<const double2 *>(p.area[0] + j + ahead));
             }
+            S2 d_rsdd, d_bias;
+            if constexpr (kSpecBypass<NS>) spec_fetch_direct<SET, NS>(p, j, d_rsdd, d_bias);      // in flight while the thread waits for the tile
             mbar_wait(&fullT[bi], use & 1);
             FastVec<kSpecV> m;
-            const LdStage<GEO::kSlotBytes> ld{ring + (size_t)s * p.t_stage_bytes + toff};
             const StPair st{j};
-            spec_t_chain<SET, NS>(m, p, ld, st, dg);
+            spec_t_tile<SET, NS>(m, p, ring + (size_t)s * p.t_stage_bytes + toff, d_rsdd, d_bias, st, dg);
             __syncwarp();
             if (lane == 0) mbar_arrive(&emptyT[bi]);
             if (__any_sync(0xffffffffu, m.bad()) && lane == 0) {
@@ -1371,7 +1436,8 @@ static bool spec_fill(const FusedPlan &p, SpecPlan &sp)
     }
     // the two carvings of the ring: as many stages as fit (2 CTAs per SM with one type, the whole SM with two)
     int t_slots = 0, u_slots = 0;
-    for (int a = 0; a < L::NT; ++a)
+    sp.t_staged = L::kStagedT;
+    for (int a = 0; a < L::kStagedT; ++a)
         if (sp.src[0][a]) t_slots = a + 1;
     for (int g = 1; g < 3; ++g)
         for (int a = 0; a < L::NUV; ++a)
@@ -1468,7 +1534,7 @@ static bool spec_build(const FusedPlan &p, const int64_t first[3], const int64_t
     if (!ok) return false;
     for (int g = 0; g < 3; ++g) {
         int n = 0;
-        for (int k = 0; k < kSpecMaxSlots; ++k) n += sp.src[g][k] != nullptr;
+        for (int k = 0; k < (g == 0 ? sp.t_staged : kSpecMaxSlots); ++k) n += sp.src[g][k] != nullptr;
         sp.tx_bytes[g] = (uint32_t)n * (uint32_t)((p.S == 1) ? SpecGeom<1>::kSlotBytes : SpecGeom<2>::kSlotBytes);
     }
     sp.area[0] = t.area;
