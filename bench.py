@@ -11,7 +11,8 @@ the diagnostics are reduced with NCCL.  One JSON line on stdout (rank 0).
 
 `value`  : device-resident throughput, CUDA events on the launching stream, max over ranks.
 `e2e`    : same metric through the C ABI with HOST (pinned) arrays: H2D + kernel + D2H inside the timed region.
-`roofline`: fused kernel only (event pairs around every launch inside the timed region) vs measured HBM peak.
+`roofline`: fused kernel only (event pairs around launches of the same loop continued after the timed region, and the
+timed region's own time per step = per launch) vs measured HBM peak.
 `cpu_baseline` / --impl reference: the CPU oracle arranged like the reference (one pass per quantity, one
 scalar call per cell), P independent ranks = all host threads, on a bounded sample of the same workload.
 """
@@ -239,9 +240,13 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="strong (default, BASELINE.json configs[3]: the 10^7-cell grid is fixed and sharded over the GPUs) or weak "
                          "(every GPU gets the workload's full cell count)")
-    ap.add_argument("--profile-stride", type=int, default=8,
-                    help="bracket every n-th fused launch with an event pair for the roofline's kernel time (an event between two "
-                         "launches switches their programmatic overlap off, so not every launch is bracketed)")
+    ap.add_argument("--profile-stride", type=int, default=4,
+                    help="bracket every n-th fused launch of the profiling loop with an event pair for the roofline's kernel time (an "
+                         "event between two launches switches their programmatic overlap off, so not every launch is bracketed)")
+    ap.add_argument("--profile-steps", type=int, default=64, help="steps of the profiling loop that follows the timed region")
+    ap.add_argument("--preheat-ms", type=float, default=0.0,
+                    help="run untimed steps for this long BEFORE the W warm-up steps (tuning aid: separates clock / TLB ramp-up from the "
+                         "step time when W and K are small; reported in config.preheat_ms)")
     ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 diagnostics exchange: peer mailboxes written by the step's kernel over NVLink (default; falls back "
                          "to NCCL when CUDA IPC is unavailable) or ncclAllReduce on a side stream")
@@ -336,17 +341,22 @@ def main():
         if dist:
             dist.barrier()
 
+    if args.preheat_ms > 0:
+        t_end = time.perf_counter() + args.preheat_ms * 1e-3
+        while time.perf_counter() < t_end:
+            for k in range(16):
+                one_step(0)
+            fc.synchronize()
     for k in range(args.warmup):
         one_step(k)
     barrier()
     launches0 = fc.info("launches")
-    fc.set_option("profile_kernel", args.profile_stride)      # event pairs around every n-th fused launch
+    fc.set_option("profile_kernel", 0)      # nothing but the K steps between the two events of the timed region (see below)
     sampler = ClockSampler(device)
     if os.environ.get("FC_BENCH_NO_SAMPLER") != "1":      # tuning aid: rule out the NVML polling as a perturbation
         sampler.start()
     barrier()
     if batched:
-        fc.set_option("profile_kernel", 0)
         fc.run_steps(600 * args.warmup, 600, 64)      # graphs captured and instantiated before the clock starts
         barrier()
         launches0 = fc.info("launches")
@@ -364,15 +374,19 @@ def main():
     clocks = sampler.stop()
     graph_launches = fc.info("graph_launches")
     launches = fc.info("launches") - launches0
-    last_t = 600 * (args.warmup + args.steps - 1)
-    if batched:      # kernel time for the roofline: a short loop of single steps with event pairs, outside the timed region
-        fc.set_option("profile_kernel", args.profile_stride)
-        for k in range(64):
-            last_t = 600 * (args.warmup + 64 + args.steps + k)
-            fc.step_all(last_t)
+    # kernel time for the roofline: the SAME step loop continued right after the timed region, every n-th launch between an
+    # event pair.  Not inside the timed region: an event between two launches switches their programmatic overlap, the early
+    # ring fill and the per-CTA hand-over off, which costs 7-18 us per bracketed launch on an 8-GPU shard (call 14: three
+    # bracketed launches in a 20-step run made ms_per_step 2-3 % worse) -- `value` must not carry the profiler's footprint.
+    k0 = args.warmup + args.steps + (64 if batched else 0)
+    last_t = 600 * (k0 - 1)
+    fc.set_option("profile_kernel", args.profile_stride)
+    for k in range(args.profile_steps):
+        last_t = 600 * (k0 + k)
+        fc.step_all(last_t)
         if diag and world > 1:
             fc.allreduce_diagnostics()
-        fc.synchronize()
+    fc.synchronize()
     kern_ms, kern_cnt = fc.kernel_time_ms()
     fc.set_option("profile_kernel", 0)
     exact_calls = fc.info("exact_path_calls")
@@ -390,6 +404,8 @@ def main():
         kern_avg_ms = kern_ms / max(kern_cnt, 1)
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step * 1e-3)
+    if kern_avg_ms <= 0.0:      # --profile-steps 0
+        kern_avg_ms = ms_per_step
 
     bytes_per_cell = fc.info("bytes_per_cell")
     peak, peak_src = measured_peaks()
@@ -399,8 +415,10 @@ def main():
     achieved_step = bytes_per_cell * max_size / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "achieved_from_ms_per_step": achieved_step, "frac_from_ms_per_step": achieved_step / peak,
-                "note": "frac: launches bracketed by event pairs (an event between two launches switches their programmatic "
-                        "overlap off); frac_from_ms_per_step: the same bytes over the timed region's time per step",
+                "note": "frac: launches bracketed by event pairs in the same step loop continued right after the timed region (an event "
+                        "between two launches switches their programmatic overlap off, so the timed region itself carries none); "
+                        "frac_from_ms_per_step: the same bytes over the timed region's time per step (one launch per step)",
+                "kernel_launches_timed": int(kern_cnt),
                 "traffic": None, "kernel": "flux_spec_kernel" if fc.info("spec_kernel") == 1 else "fused_step_kernel",
                 "kernel_ms": kern_avg_ms,
                 "algorithmic_bytes_per_cell": bytes_per_cell, "cells_per_launch": max_size, "peak_source": peak_src}
@@ -533,6 +551,7 @@ def main():
                        "parallelism": "contiguous range per GPU (fc_shard_range), %d rank(s)" % world,
                        "diagnostics_exchange": {None: "none (1 rank)", "p2p": "peer mailboxes over NVLink, posted by the step kernel's last CTA",
                                                 "nccl": "ncclAllReduce on a side stream"}[comm_used],
+                       "preheat_ms": args.preheat_ms,
                        "l2": "inputs exceed L2 (%.0f MB per step per GPU vs 126 MB), no flush" % (bytes_per_cell * max_size / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "parity": parity, "diagnostics_sample": diag_sample, "diagnostics_check": diag_check, "exact_path_calls": exact_calls,

@@ -1012,10 +1012,13 @@ __global__ void __launch_bounds__(SpecGeom<NS>::kThreads) __maxnreg__(SpecGeom<N
     __shared__ double wacc[(NS > 1 && DIAG) ? GEO::kWarps : 1][(NS > 1 && DIAG) ? (DIAG >= 2 ? 3 : 1) * kDiagAccMax : 1];
 
     const int NT = p.t_stages, NUS = p.u_stages, LT = p.t_bars, LU = p.u_bars;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kSpecMaxBars; ++s) {
+    if (threadIdx.x < kSpecMaxBars) {      // lane s arms the barriers of index s -- only those in use (a CTA's set-up is on the critical
+        const int s = threadIdx.x;          // path between two steps: the SM is full, so the next step's CTA starts when this slot frees)
+        if (s < LT) {
             mbar_init(&fullT[s], 1);                // one expect_tx arrival + the bytes
             mbar_init(&emptyT[s], GEO::kTeamWarps);      // one arrival per consumer warp of the team that took the tile
+        }
+        if (s < LU) {
             mbar_init(&fullU[s], 1);
             mbar_init(&emptyU[s], GEO::kTeamWarps);
         }
@@ -1587,6 +1590,10 @@ int spec_applicable(const FusedPlan &p, const int64_t first[3], const int64_t ce
 static bool spec_wants_dyn(const SpecPlan &sp)
 {
     if (!FC_SPEC_DYNAMIC || sp.diag) return false;
+    // Two surface types keep the static schedule unless the caller asks (option dyn_min_tiles): a t tile is 128 KB of traffic
+    // and ~9 us of a team's time there, claims are coarse against 132 tiles per CTA, and consecutive static steps hand over
+    // per CTA -- measured on C5 (10^7 cells, call 14, two repetitions): static 0.908 / 0.909 ms, dynamic 0.922 / 0.926 ms.
+    if (sp.ns > 1 && sp.dyn <= 0) return false;
     const int64_t min_tiles = sp.dyn > 0 ? sp.dyn : FC_SPEC_DYN_MIN_TILES;      // (before the launch sp.dyn carries the caller's threshold)
     return (int64_t)sp.ntiles[0] + sp.ntiles[1] + sp.ntiles[2] >= min_tiles * spec_grid(sp);
 }
