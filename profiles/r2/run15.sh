@@ -31,7 +31,7 @@ ab c4_short_preheat         $B --workload C4 --steps 20 --warmup 5 --preheat-ms 
 ab c5_short                 $B --workload C5 --steps 20 --warmup 5
 ab c5_300                   $B --workload C5 --steps 300
 N="ncu --set full --clock-control none --import-source on -k regex:flux_spec_kernel -s 3 -c 1 -f"
-C="$B --workload C5 --steps 3 --warmup 3 --profile-steps 0"
+C="$B --workload C5 --steps 3 --warmup 3 --profile-steps 0 --opt graphs=0"
 $C > $O/plain_c5.log 2>&1 && $N -o $O/r2_15_prof_c5_static $C > $O/ncu_c5.log 2>&1
 tail -3 $O/ncu_c5.log
 ls -la $O | tail -30
