@@ -207,7 +207,7 @@ __device__ __forceinline__ bool t_type_math(const FusedPlan &p, const FusedTType
     return m.bad();
 }
 
-// how often the recompute path ran (per thread = per V cells); fc_get_info("exact_path_calls")
+// how often the recompute path ran (per warp here, per thread in the specialised kernel); fc_get_info("exact_path_calls")
 __device__ unsigned long long g_exact_calls = 0ull;
 
 unsigned long long read_exact_calls()
@@ -217,21 +217,14 @@ unsigned long long read_exact_calls()
     return v + read_spec_exact_calls();
 }
 
-// recompute path (an operand left the range in which the lock-step sequences are proven): out of line, cold
-// (arguments and result by value: taking the address of the caller's register-resident structs would force
-// them into local memory on the hot path as well)
-__device__ __noinline__ TOut t_type_exact(const FusedPlan &p, int type_index, TIn in, bool has_bias)
-{
-    TOut o;
-    atomicAdd(&g_exact_calls, 1ull);
-    t_type_math<Exact>(p, p.t.ty[type_index], in, has_bias, o);
-    return o;
-}
-
-template <int SS, int DIAG, class LD>
-__device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv, DiagCtx &dg)
+// The chain of one thread's V cells, written over the arithmetic policy M: the hot instantiation (Fast) returns whether an
+// operand left the range in which the lock-step sequences are proven; the kernel then re-runs the SAME chain with the IEEE
+// policy for the whole warp (fused_cold_warp): no by-value call, no stack frame on the hot path.
+template <class M, int SS, int DIAG, class LD>
+__device__ __forceinline__ bool t_chain(const FusedPlan &p, const LD &ld, int nv, DiagCtx &dg)
 {
     const FusedT &t = p.t;
+    bool bad = false;
     const int S = SS ? SS : p.S;
     Cached<LD> cPSUR, cQATM, cTATM, cPATM, cUATM, cVATM, cAEV, cASE, cFICE, cTSUR;
     TIn in;
@@ -263,8 +256,7 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv
                 in.patm_ = cPATM.get(ld, ty.patm);
                 if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in);
             }
-            if (t_type_math<Fast>(p, ty, in, has_bias, o))        // an operand left the proven range:
-                o = t_type_exact(p, i, in, has_bias);             // redo these cells with the IEEE routines
+            bad |= t_type_math<M>(p, ty, in, has_bias, o);
             if (p.do_normal) {
                 if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
                 if (ty.m_meva != M_NONE) ld.store(ty.meva, o.meva);
@@ -315,6 +307,7 @@ __device__ __forceinline__ void t_chain(const FusedPlan &p, const LD &ld, int nv
         if (t.avg_rbbr) DIAG_COMMIT(0, DQ_RBBR, aR);
         if (t.avg_rsdr) DIAG_COMMIT(0, DQ_RSDR, aS);
     }
+    return bad;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -356,19 +349,11 @@ __device__ __forceinline__ bool uv_type_math(const FusedPlan &p, const FusedUVTy
     return m.bad();
 }
 
-__device__ __noinline__ UVOut uv_type_exact(const FusedPlan &p, int which, int type_index, UVIn in)
-{
-    UVOut o;
-    atomicAdd(&g_exact_calls, 1ull);
-    const FusedUV &g = p.uv[which - 1];
-    uv_type_math<Exact>(p, g.ty[type_index], in, g.north, o);
-    return o;
-}
-
-template <int SS, int DIAG, class LD>
-__device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, int which, const LD &ld, int nv, DiagCtx &dg)
+template <class M, int SS, int DIAG, class LD>
+__device__ __forceinline__ bool uv_chain(const FusedPlan &p, const FusedUV &g, int which, const LD &ld, int nv, DiagCtx &dg)
 {
     const int S = SS ? SS : p.S;
+    bool bad = false;
     Cached<LD> cPSUR, cUATM, cVATM, cAMOM, cFICE, cTSUR;
     UVIn in;
     V2 area;
@@ -388,7 +373,7 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
             in.vatm_ = cVATM.get(ld, ty.vatm);
             in.amom_ = cAMOM.get(ld, ty.a_mom);
             if (ty.qsur_in) in.qsur_in_ = ld.load(ty.qsur_in);
-            if (uv_type_math<Fast>(p, ty, in, g.north, o)) o = uv_type_exact(p, which, i, in);
+            bad |= uv_type_math<M>(p, ty, in, g.north, o);
             if (ty.m_qsur == M_CCLM) ld.store(ty.qsur, o.qsur);
             if (ty.m_mom != M_NONE) ld.store(ty.mom, o.mom);
             if (g.avg_qsur) avg_acc(aQ, o.qsur, fare);
@@ -425,6 +410,7 @@ __device__ __forceinline__ void uv_chain(const FusedPlan &p, const FusedUV &g, i
             if (g.avg_mom) DIAG_COMMIT(0, DQ_VMOM, aM);
         }
     }
+    return bad;
 }
 
 // L2 prefetch of the tile a later CTA will work on: one bulk prefetch per input array, issued by one thread.
@@ -498,6 +484,31 @@ struct LaunchGeom {
     int prefetch_distance;   // in blocks, 0 = off
 };
 
+// cold, out of line: every lane of the warp that called recomputes its V cells with the IEEE policy (identical bits for the
+// lanes whose operands were in range: ExactVec's exp / pow fall back to the lock-step sequences there) and, with
+// diagnostics, the warp's row is rebuilt by the same trees.  Scalars only: nothing of the hot path's state is passed.
+template <int SS, int DIAG, bool FULL>
+__device__ __noinline__ void fused_cold_warp(const FusedPlan &p, int which, int64_t j, int nv, int64_t row)
+{
+    atomicAdd(&g_exact_calls, 1ull);
+    DiagCtx dg;
+    if (DIAG) {
+        dg.base = p.diag_partials;
+        dg.rows = p.diag_rows;
+        dg.plane = (int64_t)p.diag_n * p.diag_rows;
+        dg.row = row;
+    }
+    if (FULL) {
+        const LdGlobal ld{j};
+        if (which == 0) t_chain<Exact, SS, DIAG>(p, ld, V, dg);
+        else uv_chain<Exact, SS, DIAG>(p, p.uv[which - 1], which, ld, V, dg);
+    } else {
+        const LdGuard ld{j, nv};
+        if (which == 0) t_chain<Exact, SS, DIAG>(p, ld, nv, dg);
+        else uv_chain<Exact, SS, DIAG>(p, p.uv[which - 1], which, ld, nv, dg);
+    }
+}
+
 template <int SS, int DIAG, bool FULL>
 __global__ void __launch_bounds__(kFusedThreads, kFusedMinBlocks)
 fused_step_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ LaunchGeom geo)
@@ -517,16 +528,21 @@ fused_step_kernel(const __grid_constant__ FusedPlan p, const __grid_constant__ L
         dg.plane = (int64_t)p.diag_n * p.diag_rows;
         dg.row = geo.row0 + (int64_t)b * (kFusedThreads / 32) + (threadIdx.x >> 5);
     }
+    bool bad;
     if (FULL) {        // whole 512-cell blocks only: every thread owns V valid cells
         const LdGlobal ld{j};
-        if (which == 0) t_chain<SS, DIAG>(p, ld, V, dg);
-        else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, V, dg);
+        if (which == 0) bad = t_chain<Fast, SS, DIAG>(p, ld, V, dg);
+        else bad = uv_chain<Fast, SS, DIAG>(p, p.uv[which - 1], which, ld, V, dg);
     } else {
         if (!DIAG && nv == 0) return;      // with DIAG even empty threads take part in the warp reductions
         const LdGuard ld{j, nv};
-        if (which == 0) t_chain<SS, DIAG>(p, ld, nv, dg);
-        else uv_chain<SS, DIAG>(p, p.uv[which - 1], which, ld, nv, dg);
+        if (which == 0) bad = t_chain<Fast, SS, DIAG>(p, ld, nv, dg);
+        else bad = uv_chain<Fast, SS, DIAG>(p, p.uv[which - 1], which, ld, nv, dg);
+        bad = bad && nv > 0;
     }
+    // an operand of some lane left the proven range (never with physical data): the warp redoes its cells with the IEEE
+    // routines -- same chain, same order, from global memory -- and overwrites its outputs and its diagnostics row
+    if (__any_sync(__activemask(), bad)) fused_cold_warp<SS, DIAG, FULL>(p, which, j, nv, DIAG ? dg.row : 0);
 }
 
 // diagnostics reduction, deterministic (fixed tree, independent of scheduling):
