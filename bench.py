@@ -549,7 +549,7 @@ def main():
             "config": {"workload": "%s: %s" % (args.workload, desc), "cells_per_grid": n_total, "formula_set": fset,
                        "surface_types": S, "bias": bias, "averaging": avg, "diagnostics": diag,
                        "parallelism": "contiguous range per GPU (fc_shard_range), %d rank(s)" % world,
-                       "diagnostics_exchange": {None: "none (1 rank)", "p2p": "peer mailboxes over NVLink, posted by the step kernel's last CTA",
+                       "diagnostics_exchange": {None: "none (1 rank)", "p2p": "peer mailboxes over NVLink, written by the fold of the step's diagnostics rows inside the next step's kernel",
                                                 "nccl": "ncclAllReduce on a side stream"}[comm_used],
                        "preheat_ms": args.preheat_ms,
                        "l2": "inputs exceed L2 (%.0f MB per step per GPU vs 126 MB), no flush" % (bytes_per_cell * max_size / 1e6)},
