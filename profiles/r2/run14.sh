@@ -4,7 +4,7 @@
 set -x
 export COLUMNS=200
 O=gpurun_out
-V=components/flux_calculator_b200/variants
+V=components/flux_calculator_b200/csrc/build_variants
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/r2_14_smi.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -q -rfs --tb=short --timeout 300 -p no:cacheprovider > $O/r2_14_pytest.log 2>&1
 tail -6 $O/r2_14_pytest.log
@@ -27,23 +27,23 @@ BASE=components/flux_calculator_b200/libfluxcalc_b200.so
 for rep in 1 2; do
 ab c5_base_dyn_$rep      $BASE $B --workload C5 --steps 300
 ab c5_base_static_$rep   $BASE $B --workload C5 --steps 300 --opt dyn_min_tiles=100000000
-ab c5_bypass_dyn_$rep    $V/libfluxcalc_b200_bypass2.so $B --workload C5 --steps 300
-ab c5_bypass_static_$rep $V/libfluxcalc_b200_bypass2.so $B --workload C5 --steps 300 --opt dyn_min_tiles=100000000
+ab c5_bypass_dyn_$rep    $V/libfluxcalc_bypass2.so $B --workload C5 --steps 300
+ab c5_bypass_static_$rep $V/libfluxcalc_bypass2.so $B --workload C5 --steps 300 --opt dyn_min_tiles=100000000
 done
 # one surface type: C4 and its 8-GPU shard
 ab c4_base               $BASE $B --workload C4 --no-parity
-ab c4_bypass             $V/libfluxcalc_b200_bypass3.so $B --workload C4
+ab c4_bypass             $V/libfluxcalc_bypass3.so $B --workload C4
 for rep in 1 2; do
 ab shard_base_$rep       $BASE $B --workload C4 --cells 1250000 --steps 2000 --warmup 50 --no-parity
-ab shard_bypass_$rep     $V/libfluxcalc_b200_bypass3.so $B --workload C4 --cells 1250000 --steps 2000 --warmup 50 --no-parity
+ab shard_bypass_$rep     $V/libfluxcalc_bypass3.so $B --workload C4 --cells 1250000 --steps 2000 --warmup 50 --no-parity
 done
 # what the driver's scaling run times: 20 steps after 5 warm-up steps
 for rep in 1 2 3; do
 ab shard_short_$rep      $BASE $B --workload C4 --cells 1250000 --steps 20 --warmup 5 --no-parity
 done
-ab shard_short_bypass    $V/libfluxcalc_b200_bypass3.so $B --workload C4 --cells 1250000 --steps 20 --warmup 5 --no-parity
+ab shard_short_bypass    $V/libfluxcalc_bypass3.so $B --workload C4 --cells 1250000 --steps 20 --warmup 5 --no-parity
 # the bypass builds through the parity suites
-FLUXCALC_LIB=$V/libfluxcalc_b200_bypass3.so timeout 600 python -m pytest tests/test_gpu_step_parity.py tests/test_gpu_full_size.py tests/test_step_golden.py -m gpu -q -rf --tb=short --timeout 300 -p no:cacheprovider > $O/r2_14_pytest_bypass3.log 2>&1
+FLUXCALC_LIB=$V/libfluxcalc_bypass3.so timeout 600 python -m pytest tests/test_gpu_step_parity.py tests/test_gpu_full_size.py tests/test_step_golden.py -m gpu -q -rf --tb=short --timeout 300 -p no:cacheprovider > $O/r2_14_pytest_bypass3.log 2>&1
 tail -4 $O/r2_14_pytest_bypass3.log
 # CPU arm (the reference-side lines) and the parity table
 timeout 500 python bench.py --impl reference --steps 20 --warmup 5 > $O/r2_14_c4_reference_arm.json 2> $O/r2_14_ref.err; cut -c1-250 $O/r2_14_c4_reference_arm.json
