@@ -284,7 +284,8 @@ int fc_kernel_time_ms(fc_context *ctx, double *total_ms, int64_t *count);
  *          fill its shared-memory ring before the previous step has finished -- steps write no input array; set
  *          "stream_touched" = 1 after enqueuing own work that writes bound arrays on fc_get_stream()),
  *          "graphs" (0/1, default 1: fc_run_steps replays CUDA graphs), "dyn_min_tiles" (tiles per CTA from which the
- *          specialised kernel without diagnostics claims tiles dynamically; 0 = default 48),
+ *          specialised kernel without diagnostics claims tiles dynamically; 0 = default: 48 with one surface type, never
+ *          with two),
  *          "force_generic" (0/1: use the op-list interpreter kernels instead of the fused kernel),
  *          "pin_host" (0/1: cudaHostRegister bound host arrays), "h2d_chunks" (pipeline depth of the
  *          host-pointer path), "diagnostics" (0 off, 1 area-weighted sums, 2 sums + min/max),
@@ -295,8 +296,8 @@ int fc_set_option(fc_context *ctx, const char *name, int64_t value);
 int64_t fc_get_info(const fc_context *ctx, const char *name);
 /* info names: "launches" (kernel launches issued so far), "fused" (1 if the fused kernel serves
  * fc_step_*), "bytes_per_cell" (algorithmic bytes of fc_step_all per t/u/v cell triple),
- * "h2d_bytes_per_step", "d2h_bytes_per_step", "exact_path_calls" (threads of the fused kernel that left the
- * lock-step fast path and recomputed their cells with the IEEE routines; 0 for physical data) */
+ * "h2d_bytes_per_step", "d2h_bytes_per_step", "exact_path_calls" (threads of the specialised kernel / warps of the generic
+ * fused kernel that left the lock-step fast path and recomputed their cells with the IEEE routines; 0 for physical data) */
 
 /* ------------------------------------------------------------------------------------------------
  * Diagnostics (new, additive; reproduce the reference's debug "range =" lines, flux_calculator.F90:881,
@@ -304,7 +305,9 @@ int64_t fc_get_info(const fc_context *ctx, const char *name);
  * ---------------------------------------------------------------------------------------------- */
 /* after a step with option diagnostics >= 1: out[0] = sum_j area_j * x_j; with diagnostics == 2 also
  * out[1] = min_j x_j, out[2] = max_j x_j (NaN at level 1), over the LOCAL cells (or over all ranks after
- * fc_allreduce_diagnostics) */
+ * fc_allreduce_diagnostics).  The sums are reproducible run to run (fixed trees); their last bits depend on the
+ * summation tree, i.e. on the kernel that served the step and, in host-pointer mode, on the pipeline depth
+ * ("h2d_chunks": one partial vector per chunk, combined in chunk order) -- min and max do not. */
 int fc_get_diagnostics(fc_context *ctx, int surface_type, int grid, int var_idx, double out[3]);
 
 #define FC_UNIQUE_ID_BYTES 128
@@ -314,11 +317,13 @@ int fc_allreduce_diagnostics(fc_context *ctx);                           /* nccl
 
 /* Peer-memory exchange fused into the step (preferred on one NVLink/NVSwitch node, one process per GPU): every
  * rank exports its mailbox (fc_comm_p2p_handle), the host all-gathers the handles (MPI_Allgather of
- * FC_P2P_HANDLE_BYTES per rank) and passes the rank-ordered array to fc_comm_p2p_connect.  From then on the last
- * CTA of every step's kernel stores the rank's diagnostics vector into the mailbox of every rank over NVLink;
- * fc_allreduce_diagnostics launches nothing, and fc_get_diagnostics folds the ranks' records in rank order
- * (bit-identical on all ranks).  The global values of a step can be read until two further steps were issued.
- * If fc_comm_p2p_connect fails (no IPC / no peer access) use fc_comm_init (NCCL) instead. */
+ * FC_P2P_HANDLE_BYTES per rank) and passes the rank-ordered array to fc_comm_p2p_connect.  From then on
+ * fc_allreduce_diagnostics launches nothing: it numbers an EXCHANGE, and the kernel that folds the step's diagnostics
+ * rows (the next step's kernel, or a small fold kernel when the host asks first) stores the rank's vector into the
+ * mailbox of every rank over NVLink as self-validating 8-byte words.  fc_get_diagnostics folds the ranks' records in
+ * rank order (bit-identical on all ranks).  Mailboxes are keyed by exchange (slot = exchange mod 8): steps whose
+ * global values nobody asked for post nothing, and the values of an exchange can be read until eight further
+ * exchanges were issued.  If fc_comm_p2p_connect fails (no IPC / no peer access) use fc_comm_init (NCCL) instead. */
 #define FC_P2P_HANDLE_BYTES 64
 int fc_comm_p2p_handle(fc_context *ctx, char handle[FC_P2P_HANDLE_BYTES]);
 int fc_comm_p2p_connect(fc_context *ctx, const char *handles /* nranks x FC_P2P_HANDLE_BYTES */, int rank, int nranks);
