@@ -1,13 +1,14 @@
 // p2p_comm.cu -- multi-GPU exchange of the diagnostics vector over NVLink peer memory, fused into the step.
 //
-// One process per GPU.  Every rank allocates a mailbox (2 parities x nranks DiagMail records), exports it as a CUDA
+// One process per GPU.  Every rank allocates a mailbox (kMailDepth slots x nranks DiagMail records), exports it as a CUDA
 // IPC handle; the host exchanges the handles (MPI_Allgather in the Fortran host, torch.distributed/gloo in bench.py)
-// and every rank maps all mailboxes.  From then on the last CTA of each step's kernel stores the rank's result
-// vector into the mailbox of every rank with plain peer stores of self-validating 8-byte words (32 data bits + the
-// step's 32-bit sequence number; no fence, no flag store) (spec_kernel.cu: diag_finish; other paths:
-// diag_post_kernel).  No collective launch, no extra kernel, nothing competing with the persistent kernel for an SM.  fc_get_diagnostics folds the nranks records in
-// rank order on the host, so all ranks see bit-identical global sums.  NCCL (nccl_dyn.cu) remains as the fallback
-// when IPC is unavailable.
+// and every rank maps all mailboxes.  From then on the kernel that folds a step's diagnostics rows into its result
+// vector -- the producer warps of the NEXT step's kernel, or the small fold kernel when the host asks first
+// (spec_kernel.cu: diag_fold_slot; other paths: diag_post_kernel) -- stores that vector into the mailbox of every rank
+// with plain peer stores of self-validating 8-byte words (32 data bits + the exchange's 32-bit sequence number; no
+// fence, no flag store), one lane per (rank, plane).  No collective launch, nothing competing with the persistent
+// kernel for an SM.  fc_get_diagnostics folds the nranks records in rank order on the host, so all ranks see
+// bit-identical global sums.  NCCL (nccl_dyn.cu) remains as the fallback when IPC is unavailable.
 //
 // Records are keyed by EXCHANGE, not by step: fc_allreduce_diagnostics (a collective: every rank calls it for the same
 // steps) numbers the exchanges, and the record of exchange e lives in slot e mod kMailDepth of every mailbox.  Steps
