@@ -3,8 +3,10 @@
 //  fused_step_kernel   generic fused pass (any number of surface types, any method mix, averaging): t-, u-
 //                      and v-grid chains of every surface type in one pass over SoA fields, intermediates in
 //                      registers, 128-bit coalesced loads/stores, per-warp diagnostics partials.  Also the
-//                      guarded variant for ragged remainders / misaligned arrays.  The specialised persistent
-//                      kernel of spec_kernel.cu takes over for the canonical single-surface-type plans.
+//                      guarded variant for ragged remainders / misaligned arrays.  The chain is a template over the
+//                      arithmetic policy: the hot instantiation flags operands outside the proven range, the warp
+//                      then re-runs it out of line with the IEEE policy.  The specialised persistent kernel of
+//                      spec_kernel.cu takes over for the canonical plans with one or two surface types.
 //  oplist_kernel       interpreter for the reference's pass sequence (exact semantics for aliased
 //                      outputs / unfused calc_* calls / the Level-1 flux_lib array routines).
 //  diag_finalize, transpose_corrections, regrid_csr: small helpers.
