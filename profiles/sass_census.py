@@ -42,9 +42,10 @@ def demangle(n):
 print("# SASS census of libfluxcalc_b200.so (sm_100a)\n")
 print("No tensor-core / TMEM mnemonics anywhere (the path is elementwise FP64). `UBLKCP` = `cp.async.bulk` (TMA bulk copy),")
 print("`SYNCS` = mbarrier arrive / try_wait / expect_tx, `MUFU` = RCP64H / RSQ64H seeds of the lock-step division and square root.")
-print("Counts are per kernel entry INCLUDING its out-of-line cold subroutines (the IEEE recompute paths, which hold most of the")
-print("`LDL`/`STL` and all of the stack of the one-surface-type kernels); `fused_step_kernel<0,0,true>`: about 30 of its 210 local-memory")
-print("instructions sit on the hot path (before the first `EXIT`), the rest in `fused_cold_warp` and the IEEE division / exp / pow calls.\n")
+print("Counts are per kernel entry INCLUDING its out-of-line subroutines (the IEEE recompute paths and the diagnostics fold). The")
+print("one-surface-type `flux_spec_kernel`s touch local memory only around the calls of those routines, never in the tile loops;")
+print("`fused_step_kernel<0,0,true>`: about 30 of its 210 local-memory instructions sit on the hot path (before the first `EXIT`), the")
+print("rest in `fused_cold_warp` and the IEEE division / exp / pow calls.\n")
 print("| kernel | regs | stack B | static smem B | instr | " + " | ".join(WATCH) + " |")
 print("|---|---|---|---|---|" + "---|" * len(WATCH))
 for name in sorted(hist, key=demangle):
