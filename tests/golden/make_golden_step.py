@@ -463,6 +463,62 @@ def scenario_defs():
     return S
 
 
+def scenario_defs_extra():
+    """More formula-set x surface-type combinations of the reference's host code, for the ORACLE only (CPU tests): they widen
+    what pins the oracle without adding untried registry shapes to the GPU suite (tests/golden/step_golden_extra.json)."""
+    S = []
+    atm_t = ["PSUR", "PATM", "QATM", "TATM", "UATM", "VATM", "RSDD", "ALBA"]
+    two = {1: ["TSUR", "FICE", "ALBE", "FARE"], 2: ["TSUR", "FICE", "ALBE", "FARE"]}
+    # e1: RCO set (Meier et al. 1999), open water + ice, area-fraction averages of every sent flux
+    S.append(dict(
+        name="rco_s2_avg", sizes=(13, 13, 13), steps=2, timestep=600, init_date=19610301, bias=False,
+        nml={
+            "name_atmos_var_t": names(atm_t), "name_atmos_var_u": names(["UATM", "VATM"]), "name_atmos_var_v": names(["UATM", "VATM"]),
+            "name_bottom_var_t": bottom(1, two),
+            "name_bottom_var_u": bottom(1, {1: ["FARE"], 2: ["FARE"]}), "name_bottom_var_v": bottom(1, {1: ["FARE"], 2: ["FARE"]}),
+            "which_spec_vapor_surface_t": methods(1, {1: "CCLM", 2: "CCLM"}),
+            "which_flux_mass_evap": methods(1, {1: "RCO", 2: "RCO"}), "which_flux_heat_latent": methods(1, {1: "water", 2: "ice"}),
+            "which_flux_heat_sensible": methods(1, {1: "RCO", 2: "RCO"}), "which_flux_momentum": methods(1, {1: "RCO", 2: "RCO"}),
+            "which_flux_radiation_blackbody": methods(1, {1: "StBo", 2: "StBo"}),
+            "name_send_t": names(["MEVA", "HLAT", "HSEN", "RBBR", "RSDR"]), "name_send_u": names(["UMOM"]), "name_send_v": names(["VMOM"]),
+        }))
+    # e2: MOM5 transfer coefficients per surface type (CMOI != CHEA), open water + ice, bias across the turn of the year
+    mom_t = {1: ["TSUR", "FICE", "ALBE", "FARE", "CMOI", "CHEA"], 2: ["TSUR", "FICE", "ALBE", "FARE", "CMOI", "CHEA"]}
+    mom_uv = {1: ["TSUR", "FICE", "FARE", "CMOM"], 2: ["TSUR", "FICE", "FARE", "CMOM"]}
+    S.append(dict(
+        name="mom5_s2_ice_bias", sizes=(11, 12, 13), steps=3, timestep=43200, init_date=19611231, bias=True,
+        nml={
+            "name_atmos_var_t": names(atm_t), "name_atmos_var_u": names(["PSUR", "UATM", "VATM", "TATM"]),
+            "name_atmos_var_v": names(["PSUR", "UATM", "VATM", "TATM"]),
+            "name_bottom_var_t": bottom(1, mom_t), "name_bottom_var_u": bottom(1, mom_uv), "name_bottom_var_v": bottom(1, mom_uv),
+            "which_spec_vapor_surface_t": methods(1, {1: "CCLM", 2: "CCLM"}), "which_spec_vapor_surface_u": methods(1, {1: "CCLM", 2: "CCLM"}),
+            "which_spec_vapor_surface_v": methods(1, {1: "CCLM", 2: "CCLM"}),
+            "which_flux_mass_evap": methods(1, {1: "MOM5", 2: "MOM5"}), "which_flux_heat_latent": methods(1, {1: "water", 2: "ice"}),
+            "which_flux_heat_sensible": methods(1, {1: "MOM5", 2: "MOM5"}), "which_flux_momentum": methods(1, {1: "MOM5", 2: "MOM5"}),
+            "which_flux_radiation_blackbody": methods(1, {1: "StBo", 2: "StBo"}),
+            "name_send_t": names(["MEVA", "HLAT", "HSEN", "RBBR", "RSDR"]), "name_send_u": names(["UMOM"]), "name_send_v": names(["VMOM"]),
+        }))
+    # e3: five surface types (open water + four ice classes), CCLM set, averages of the fluxes and of a pass-through variable
+    five = {i: ["TSUR", "FICE", "ALBE", "FARE"] for i in range(1, 6)}
+    fiveuv = {i: ["TSUR", "FICE", "FARE"] for i in range(1, 6)}
+    allc = {i: "CCLM" for i in range(1, 6)}
+    S.append(dict(
+        name="cclm_s5_avg_bias", sizes=(10, 10, 10), steps=2, timestep=600, init_date=19610831, bias=True,
+        nml={
+            "name_atmos_var_t": names(atm_t + ["AMOI"]), "name_atmos_var_u": names(["PSUR", "UATM", "VATM", "AMOM", "TATM"]),
+            "name_atmos_var_v": names(["PSUR", "UATM", "VATM", "AMOM", "TATM"]),
+            "name_bottom_var_t": bottom(1, five), "name_bottom_var_u": bottom(1, fiveuv), "name_bottom_var_v": bottom(1, fiveuv),
+            "which_spec_vapor_surface_t": methods(1, allc), "which_spec_vapor_surface_u": methods(1, allc),
+            "which_spec_vapor_surface_v": methods(1, allc),
+            "which_flux_mass_evap": methods(1, allc), "which_flux_heat_latent": methods(1, {1: "water", 2: "ice", 3: "ice", 4: "ice", 5: "ice"}),
+            "which_flux_heat_sensible": methods(1, allc), "which_flux_momentum": methods(1, allc),
+            "which_flux_radiation_blackbody": methods(1, {i: "StBo" for i in range(1, 6)}),
+            "name_send_t": names(["MEVA", "HLAT", "HSEN", "RBBR", "RSDR", "TSUR"]),
+            "name_send_u": names(["UMOM"]), "name_send_v": names(["VMOM"]),
+        }))
+    return S
+
+
 def run_scenario(ref, sd, seed):
     R = Reference(ref)
     nml = dict(sd["nml"])
@@ -534,12 +590,17 @@ def run_scenario(ref, sd, seed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--out", default=os.path.join(HERE, "step_golden.json"))
+    ap.add_argument("--set", default="main", choices=["main", "extra"],
+                    help="main: step_golden.json (oracle on CPU + CUDA library with -m gpu); extra: step_golden_extra.json (oracle only)")
+    ap.add_argument("--out", default=None)
     a = ap.parse_args()
+    if a.out is None:
+        a.out = os.path.join(HERE, "step_golden.json" if a.set == "main" else "step_golden_extra.json")
     scen = []
     files = None
-    for k, sd in enumerate(scenario_defs()):
-        res = run_scenario(a.ref, sd, 0x5EEDF1C5 + k)
+    defs, seed0 = (scenario_defs(), 0x5EEDF1C5) if a.set == "main" else (scenario_defs_extra(), 0x5EEDF1C5 + 100)
+    for k, sd in enumerate(defs):
+        res = run_scenario(a.ref, sd, seed0 + k)
         if isinstance(res, tuple):
             res, R = res
             files = R.files

@@ -16,8 +16,11 @@ fh = float.fromhex
 DIRECTION = {(2, 1): 0, (3, 1): 1, (1, 2): 2, (1, 3): 3}      # (from grid, to grid) -> fc_set_regrid_matrix direction
 
 
-def scenarios():
-    with open(GOLDEN) as f:
+GOLDEN_EXTRA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "step_golden_extra.json")      # oracle only
+
+
+def scenarios(path=GOLDEN):
+    with open(path) as f:
         return json.load(f)["scenarios"]
 
 

@@ -41,13 +41,38 @@ def test_oracle_sends_what_the_reference_sends(name, explicit):
     assert checked[1] == len(s["sent"]) and checked[0] > 0
 
 
+EXTRA = {s["name"]: s for s in step_replay.scenarios(step_replay.GOLDEN_EXTRA)}
+
+
+@pytest.mark.parametrize("name", sorted(EXTRA))
+@pytest.mark.parametrize("explicit", [True, False])
+def test_oracle_sends_what_the_reference_sends_extra(name, explicit):
+    """tests/golden/step_golden_extra.json (make_golden_step.py --set extra): RCO with two surface types, MOM5 coefficients
+    per type with ice and the bias across the turn of the year, five surface types -- the interpreted reference against the
+    oracle only, bit for bit (these registry shapes are not replayed through the CUDA library)"""
+    s = EXTRA[name]
+    assert s.get("sent"), name
+    orc = Oracle(s["grid_size"], s["num_surface_types"])
+    rp = step_replay.Replay(s, orc, explicit_allocated=explicit)
+    n = [0, 0]
+
+    def compare(put, got, key):
+        ref = step_replay.arr(put["values"])
+        known = ~np.isnan(ref)
+        assert np.array_equal(got[known], ref[known]), (name, put["name"], put["time"])
+        n[0] += int(known.sum())
+        n[1] += 1
+    rp.run(compare)
+    assert n[1] == len(s["sent"]) and n[0] > 0
+
+
 def test_bias_month_comes_from_the_reference_python_helper():
     """the months the interpreted reference obtained from pyfort/datetime_helpers.py == the oracle's calendar"""
     import ctypes as C
     from oracle_py import load
     lib = load()
     lib.orc_current_month.restype = C.c_int
-    for s in SCEN.values():
+    for s in list(SCEN.values()) + list(EXTRA.values()):
         for k, m in enumerate(s.get("months") or []):
             assert lib.orc_current_month(s["init_date"], k * s["timestep"]) == m
 
