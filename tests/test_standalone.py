@@ -8,6 +8,7 @@ import pytest
 import step_replay
 
 SCEN = {s["name"]: s for s in step_replay.scenarios()}
+EXTRA = {s["name"]: s for s in step_replay.scenarios(step_replay.GOLDEN_EXTRA)}      # set-up only (no device needed)
 
 
 def _nml(tmp_path, s):
@@ -16,9 +17,9 @@ def _nml(tmp_path, s):
     return p
 
 
-@pytest.mark.parametrize("name", [n for n, s in SCEN.items() if "registry_after_setup" in s])
+@pytest.mark.parametrize("name", [n for n, s in SCEN.items() if "registry_after_setup" in s] + sorted(EXTRA))
 def test_registry_matches_the_reference(fcmod, tmp_path, name):
-    s = SCEN[name]
+    s = SCEN.get(name) or EXTRA[name]
     got = fcmod.namelist_registry(_nml(tmp_path, s), 1, s["grid_size"])
     assert got["num_surface_types"] == s["num_surface_types"]
     ref = {(r["type"], r["grid"], r["var"]): r for r in s["registry_after_setup"]}
