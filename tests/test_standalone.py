@@ -106,3 +106,40 @@ def test_namelist_drives_the_time_loop(fcmod, tmp_path, name):
                         check_field(o["var"], o["array"][known], ref[known], exact=o["var"] in exact_vars, scale=scale)
     assert k == len(puts)
     fc.close()
+
+
+def test_compact_namelist_syntax_builds_the_same_registry(fcmod, tmp_path):
+    """the namelist written the way a person writes it -- array sections with value lists, repeat counts, several assignments
+    per line, a one-line &correctionsctl group -- against the one-assignment-per-line text of the golden
+    scenario with the same content: identical registry, field lists and OASIS names"""
+    s = SCEN["cclm_s1_bias"]
+    compact = """&input
+  timestep=43200, num_timesteps=3, name_atmos_model='CCLM', name_bottom_model(1)='MOM5', letter_bottom_model(1)='M',
+  num_tasks_per_model(1)=1,
+  name_atmos_var_t(1:9)='PSUR','PATM','QATM','TATM','UATM','VATM','RSDD','ALBA','AMOI',
+  name_atmos_var_u(1:5)='PSUR','UATM','VATM','AMOM','TATM',  name_atmos_var_v(1:5)='PSUR','UATM','VATM','AMOM','TATM',
+  name_bottom_var_t(1,1,1:3)='TSUR','FICE','ALBE', val_bottom_var_t(1,1,2)=0.0,
+  name_bottom_var_u(1,1,1:2)='TSUR','FICE', val_bottom_var_u(1,1,2)=0.0,
+  name_bottom_var_v(1,1,1:2)='TSUR','FICE', val_bottom_var_v(1,1,2)=0.0,
+  which_spec_vapor_surface_t(1,1)='CCLM', which_spec_vapor_surface_u(1,1)='CCLM', which_spec_vapor_surface_v(1,1)='CCLM',
+  which_flux_mass_evap(1,1)='CCLM', which_flux_heat_latent(1,1)='water', which_flux_heat_sensible(1,1)='CCLM',
+  which_flux_momentum(1,1)='CCLM', which_flux_radiation_blackbody(1,1)='StBo',   ! one surface type: open water
+  name_send_t(1:5)='MEVA','HLAT','HSEN','RBBR','RSDR', name_send_u(1)='UMOM', name_send_v(1)='VMOM',
+  send_uniform_t(1,1:5)=5*.TRUE., send_uniform_u(1,1)=.TRUE., send_uniform_v(1,1)=.TRUE.,
+  send_to_atmos_t(1:5)=5*.FALSE., send_to_bottom_u(1,1)=.FALSE., send_to_bottom_v(1,1)=.FALSE.
+/
+&correctionsctl  init_date=19610131, lcorrections(1)=.TRUE. /
+"""
+    p = tmp_path / "compact.nml"
+    p.write_text(compact)
+    a = fcmod.namelist_registry(p, 1, s["grid_size"])
+    b = fcmod.namelist_registry(_nml(tmp_path, s), 1, s["grid_size"])
+    key = lambda r: (r["type"], r["grid"], r["var"])      # noqa: E731
+    assert sorted(map(key, a["registry"])) == sorted(map(key, b["registry"]))
+    ra, rb = {key(r): r for r in a["registry"]}, {key(r): r for r in b["registry"]}
+    for k in ra:
+        assert (ra[k]["allocated"], ra[k]["fill"], sorted(ra[k]["regrid_to"])) == (rb[k]["allocated"], rb[k]["fill"], sorted(rb[k]["regrid_to"])), k
+    groups = lambda reg: sorted(sorted(k for k in reg if reg[k]["storage"] == st) for st in {r["storage"] for r in reg.values()})      # noqa: E731
+    assert groups(ra) == groups(rb)
+    strip = lambda lst: [{k: f[k] for k in ("name", "grid", "early", "type", "var")} for f in lst]      # noqa: E731
+    assert strip(a["input_fields"]) == strip(b["input_fields"]) and strip(a["output_fields"]) == strip(b["output_fields"])
